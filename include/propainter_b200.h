@@ -1,0 +1,110 @@
+/* propainter_b200 -- C ABI of the sm_100a hot-path kernels (libpropainter_b200.so).
+ *
+ * The reference (sczhou/ProPainter) has no native code and no FFI: every op below replaces a
+ * *library call site* in the reference's Python (torch / torchvision), cited per entry point.
+ * A reference-side binding is a ctypes stub.  Conventions:
+ *   - plain pointers + sizes, device pointers unless noted; no torch types
+ *   - returns 0 or a negative PP_ERR_* code; never throws, never allocates, never synchronises
+ *   - caller owns every buffer incl. workspace (size from pp_<op>_workspace_bytes)
+ *   - stream-ordered on `stream`, re-entrant across streams, no global mutable state
+ * Layouts: "planar" = [n][c][H][W] (reference API boundary); "pixel-major" = [n][H][W][ld], ld >= C
+ * given explicitly so ops can read / write channel slices of wider concat buffers.  fp32 throughout.
+ */
+#ifndef PROPAINTER_B200_H
+#define PROPAINTER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+int pp_abi_version(void);
+const char* pp_error_string(int code);
+
+/* ---- RAFT correlation (RAFT/corr.py) -------------------------------------------------------- */
+/* CorrBlock.corr :52-60.  fmap pixel-major [frames][h*w][D]; pair p correlates frame idx1[p] with
+ * idx2[p] (device int32 arrays).  Writes level 0: [n_pairs][h*w][h][ld0], ld0 = roundup4(w). */
+int pp_corr_build(const float* fmap, int D, const int* idx1, const int* idx2, int n_pairs, float* lvl0, int h, int w,
+                  cudaStream_t stream);
+/* CorrBlock.__init__ :25-27 (3x avg_pool2d).  levels[l]: [planes][h>>l][roundup4(w>>l)] (host array of
+ * 4 device pointers); level 0 must be filled. */
+int pp_corr_pool_pyramid(float* const* levels, long planes, int h, int w, cudaStream_t stream);
+/* CorrBlock.__call__ :29-50 + bilinear_sampler RAFT/utils/utils.py:57-71.
+ * coords [n_pairs*h*w][2] (x,y) -> out pixel-major [n_pairs*h*w][324]. */
+int pp_corr_lookup(const float* const* levels, const float* coords, float* out, long n_pairs, int h, int w,
+                   cudaStream_t stream);
+/* RAFT.upsample_flow RAFT/raft.py:73-84.  mask pixel-major [n*h*w][ld_mask>=576] (unscaled conv output,
+ * mask_scale = 0.25 from update.py:135); flow_lr [n][h][w][2]; out planar [n][2][8h][8w]. */
+int pp_convex_upsample(const float* mask, int ld_mask, float mask_scale, const float* flow_lr, float* out, int n,
+                       int h, int w, cudaStream_t stream);
+
+/* ---- propagation ---------------------------------------------------------------------------- */
+/* InpaintGenerator.img_propagation model/propainter.py:315-317 (BidirectionalPropagation :104-190,
+ * learnable=False; flow_warp model/modules/flow_loss_utils.py:6-45; fbConsistencyCheck :22-31).
+ * All planar, batch 1: frames [t][3][H][W], flows [t-1][2][H][W], masks [t][1][H][W]. nearest: 1|0. */
+size_t pp_img_prop_scan_workspace_bytes(int t, int H, int W);
+int pp_img_prop_scan(const float* frames, const float* flows_f, const float* flows_b, const float* masks,
+                     float* out_frames, float* out_masks, void* workspace, size_t ws_bytes, int t, int H, int W,
+                     int nearest, cudaStream_t stream);
+/* One step's prologue of BidirectionalPropagation(learnable=True) model/propainter.py:144-166:
+ * fb-check + bilinear flow_warp + the two torch.cat's.  Pixel-major features (C channels), flows /
+ * masks pixel-interleaved [h][w][2].  cond = [cur | warped | fx fy | valid | m0 m1 | 0..],
+ * bb = [cur | <slot for the aligned feature> | m0 m1 | 0..]; first!=0: no cond, slot := cur. */
+int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int ld_prop, const float* fprop,
+                 const float* fcheck, const float* mcur, float* cond, int ld_cond, float* bb, int ld_bb, int h, int w,
+                 int C, int first, cudaStream_t stream);
+/* DeformableAlignment.forward model/propainter.py:57-69 and SecondOrderDeformableAlignment.forward
+ * model/recurrent_flow_completion.py:31-44 after the conv_offset stack (torchvision.ops.deform_conv2d,
+ * 3x3/s1/p1, 16 deform groups).  x pixel-major [H*W][ld_x] (Cin), o = raw conv_offset output
+ * [H*W][ld_o>=432], flow [H*W][2] or NULL, w_packed [9*Cin][128] (row = tap*Cin + c), out [H*W][ld_out]. */
+int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
+                    const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin, int Cout,
+                    cudaStream_t stream);
+
+/* ---- generator glue ------------------------------------------------------------------------- */
+/* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar
+ * [lt-1][2][H][W] -> [lt-1][H/4][W/4][2] (/4); masks planar [>=lt][1][H][W] -> pmask [lt][H/4][W/4][2]. */
+int pp_gen_prep(const float* flows_f, const float* flows_b, const float* masks_in, const float* masks_upd, float* dsf,
+                float* dsb, float* pmask, int lt, int H, int W, cudaStream_t stream);
+/* max_pool (model/propainter.py:349-350) + window max-pool/sum (sparse_transformer.py:224-229):
+ * flags[nwh*nww] = 1 if any local frame has mask inside the window. */
+int pp_window_mask(const float* pmask, int lt, int h, int w, int fh, int fw, int nwh, int nww, int* flags,
+                   cudaStream_t stream);
+
+typedef struct PPAttnParams {
+  const float* qkv;     /* [t][NT][ld_qkv]: Q at +0, K at +C, V at +2C (padded token grid, NT tokens/frame) */
+  const float* pool;    /* [t][NP][ld_pool]: pooled K at +0, V at +C */
+  const int* key_tok;   /* [n_windows][NKO] token index of own (first WN) + rolled keys */
+  const int* flags;     /* [n_windows] window masked? */
+  float* out;           /* [t][NT][ld_out] head-concatenated attention output */
+  int ld_qkv, ld_pool, ld_out;
+  int t, NT, WN, NKO, NP, C;
+  int kf_start, kf_step, nkf;   /* key frames T_ind = kf_start + i*kf_step, i < nkf */
+  float scale_log2;             /* log2(e)/sqrt(head_dim) */
+} PPAttnParams;
+/* SparseWindowAttention.forward model/modules/sparse_transformer.py:177-275 (between q/k/v and proj). */
+int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream);
+
+/* FusionFeedForward.forward model/modules/sparse_transformer.py:81-100: fold -> /normalizer -> unfold -> GELU.
+ * Y,Z [frames*fh*fw][ld], hidden columns tap-major (tap*CH + c). */
+size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH);
+int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH, void* workspace,
+                       size_t ws_bytes, cudaStream_t stream);
+
+/* ---- driver-side pixel ops (inference_propainter.py) ----------------------------------------- */
+/* to_tensors()(frames)*2-1  core/utils.py:130-170 + inference_propainter.py:264: uint8 [T][H][W][3] -> planar float */
+int pp_u8_to_frames(const uint8_t* src, float* dst, int T, int H, int W, cudaStream_t stream);
+#define PP_MAX_WINDOW 32
+typedef struct PPWindowIds { int n; int frame[PP_MAX_WINDOW]; int first[PP_MAX_WINDOW]; } PPWindowIds;
+/* inference_propainter.py:437-450: pred planar [n][3][H][W] in (-1,1), masks planar [T][1][H][W],
+ * ori/comp uint8 [T][H][W][3]; ids (host struct): target frame + first-visit flag per local frame. */
+int pp_composite_blend_u8(const float* pred, const float* masks, const uint8_t* ori, uint8_t* comp,
+                          const PPWindowIds* ids, int H, int W, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

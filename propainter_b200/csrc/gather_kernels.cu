@@ -1,0 +1,332 @@
+// HBM/L2-bound gather, stencil and elementwise kernels of the ProPainter hot path (sm_100a).
+// One thread (or one warp) per output element; the per-element rules live in pp_elem.cuh.
+#include "pp_elem.cuh"
+#include "../../include/propainter_b200.h"
+
+#define PP_LAUNCH_CHECK() do { if (cudaPeekAtLastError() != cudaSuccess) return PP_ERR_LAUNCH; } while (0)
+
+static inline int pp_blocks(long n, int per) { return (int)((n + per - 1) / per); }
+
+// ================================================================ image propagation scan
+__global__ void __launch_bounds__(256) k_imgprop_step(int H, int W, const float* __restrict__ cur,
+    const float* __restrict__ mcur, const float* __restrict__ prev, const float* __restrict__ mprev,
+    const float* __restrict__ fprop, const float* __restrict__ fcheck, float* __restrict__ out,
+    float* __restrict__ mout, int nearest) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < H * W) pp_imgprop_pixel(pix, H, W, cur, mcur, prev, mprev, fprop, fcheck, out, mout, nearest);
+}
+
+extern "C" size_t pp_img_prop_scan_workspace_bytes(int t, int H, int W) {
+  return (size_t)t * 4 * H * W * sizeof(float);
+}
+
+// replaces InpaintGenerator.img_propagation (model/propainter.py:315-317 -> :104-190, learnable=False)
+extern "C" int pp_img_prop_scan(const float* frames, const float* flows_f, const float* flows_b,
+                                const float* masks, float* out_frames, float* out_masks, void* workspace,
+                                size_t ws_bytes, int t, int H, int W, int nearest, cudaStream_t stream) {
+  if (t < 1 || H < 2 || W < 2) return PP_ERR_SHAPE;
+  if (ws_bytes < pp_img_prop_scan_workspace_bytes(t, H, W)) return PP_ERR_WORKSPACE;
+  const long HW = (long)H * W;
+  float* bf = (float*)workspace;             // backward-scan frames [t][3][HW]
+  float* bm = bf + (long)t * 3 * HW;         // backward-scan masks  [t][HW]
+  const int blocks = pp_blocks(HW, 256);
+  // backward scan: t-1 -> 0, propagates along the forward flows
+  cudaMemcpyAsync(bf + (long)(t - 1) * 3 * HW, frames + (long)(t - 1) * 3 * HW, 3 * HW * sizeof(float),
+                  cudaMemcpyDeviceToDevice, stream);
+  cudaMemcpyAsync(bm + (long)(t - 1) * HW, masks + (long)(t - 1) * HW, HW * sizeof(float),
+                  cudaMemcpyDeviceToDevice, stream);
+  for (int i = t - 2; i >= 0; --i)
+    k_imgprop_step<<<blocks, 256, 0, stream>>>(H, W, frames + (long)i * 3 * HW, masks + (long)i * HW,
+        bf + (long)(i + 1) * 3 * HW, bm + (long)(i + 1) * HW, flows_f + (long)i * 2 * HW,
+        flows_b + (long)i * 2 * HW, bf + (long)i * 3 * HW, bm + (long)i * HW, nearest);
+  // forward scan: consumes the backward scan's frames and masks (:138-139)
+  cudaMemcpyAsync(out_frames, bf, 3 * HW * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  cudaMemcpyAsync(out_masks, bm, HW * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  for (int i = 1; i < t; ++i)
+    k_imgprop_step<<<blocks, 256, 0, stream>>>(H, W, bf + (long)i * 3 * HW, bm + (long)i * HW,
+        out_frames + (long)(i - 1) * 3 * HW, out_masks + (long)(i - 1) * HW, flows_b + (long)(i - 1) * 2 * HW,
+        flows_f + (long)(i - 1) * 2 * HW, out_frames + (long)i * 3 * HW, out_masks + (long)i * HW, nearest);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ learnable propagation: cond assembly
+// One warp per pixel: lane 0 evaluates the sampling coordinate + fb-consistency and broadcasts it by
+// shuffle; the 32 lanes then gather the 4 bilinear corners as float4 channel vectors (coalesced 512 B
+// per corner for C=128) and write the concat buffers the offset-net / backbone convs consume.
+__global__ void __launch_bounds__(256) k_prop_cond(int h, int w, int C, const float* __restrict__ cur, int ld_cur,
+    const float* __restrict__ prop, int ld_prop, const float* __restrict__ fprop,
+    const float* __restrict__ fcheck, const float* __restrict__ mcur, float* __restrict__ cond, int ld_cond,
+    float* __restrict__ bb, int ld_bb, int first) {
+  const int lane = threadIdx.x & 31;
+  const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= (long)h * w) return;
+  const int y = (int)(pix / w), x = (int)(pix - (long)y * w);
+  float ix = 0.f, iy = 0.f, valid = 0.f, fx = 0.f, fy = 0.f;
+  if (!first) {
+    if (lane == 0) {
+      PPCond c = pp_cond_pixel(y, x, h, w, fprop, fcheck);
+      ix = c.ix; iy = c.iy; valid = c.valid; fx = c.fx; fy = c.fy;
+    }
+    ix = __shfl_sync(0xffffffffu, ix, 0); iy = __shfl_sync(0xffffffffu, iy, 0);
+    valid = __shfl_sync(0xffffffffu, valid, 0);
+    fx = __shfl_sync(0xffffffffu, fx, 0); fy = __shfl_sync(0xffffffffu, fy, 0);
+  }
+  const PPTaps t = first ? PPTaps() : pp_taps(ix, iy, h, w);
+  const float* curp = cur + pix * ld_cur;
+  float* bbp = bb + pix * ld_bb;
+  float* cdp = first ? nullptr : cond + pix * ld_cond;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(curp + c);
+    *reinterpret_cast<float4*>(bbp + c) = v;
+    if (first) {
+      *reinterpret_cast<float4*>(bbp + C + c) = v;          // feat_prop = feat_current (:141-143)
+    } else {
+      *reinterpret_cast<float4*>(cdp + c) = v;
+      *reinterpret_cast<float4*>(cdp + C + c) = pp_tap_nhwc4(prop, ld_prop, w, t, c);
+    }
+  }
+  if (lane == 0) {
+    const float m0 = mcur[2 * pix], m1 = mcur[2 * pix + 1];
+    bbp[2 * C] = m0; bbp[2 * C + 1] = m1;
+    for (int c = 2 * C + 2; c < ld_bb; ++c) bbp[c] = 0.f;
+    if (!first) {
+      cdp[2 * C] = fx; cdp[2 * C + 1] = fy; cdp[2 * C + 2] = valid; cdp[2 * C + 3] = m0; cdp[2 * C + 4] = m1;
+      for (int c = 2 * C + 5; c < ld_cond; ++c) cdp[c] = 0.f;
+    }
+  }
+}
+
+// replaces the flow_warp + fbConsistencyCheck + torch.cat prologue of one step of
+// BidirectionalPropagation(learnable=True) (model/propainter.py:144-166)
+extern "C" int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int ld_prop, const float* fprop,
+                            const float* fcheck, const float* mcur, float* cond, int ld_cond, float* bb, int ld_bb,
+                            int h, int w, int C, int first, cudaStream_t stream) {
+  if (C % 4 || ld_cur % 4 || ld_prop % 4 || ld_cond % 4 || ld_bb % 4) return PP_ERR_ALIGN;
+  if (ld_bb < 2 * C + 2 || (!first && ld_cond < 2 * C + 5)) return PP_ERR_SHAPE;
+  const long n = (long)h * w;
+  k_prop_cond<<<pp_blocks(n, 8), 256, 0, stream>>>(h, w, C, cur, ld_cur, prop, ld_prop, fprop, fcheck, mcur, cond,
+                                                    ld_cond, bb, ld_bb, first);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ RAFT correlation pyramid + lookup
+__global__ void __launch_bounds__(256) k_corr_pool(const float* __restrict__ src, float* __restrict__ dst, long planes,
+                                                   int Hs, int lds, int Hd, int Wd, int ldd) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long per = (long)Hd * Wd;
+  if (i >= planes * per) return;
+  long p = i / per; int r = (int)(i - p * per); int y = r / Wd, x = r - y * Wd;
+  dst[p * (long)Hd * ldd + (long)y * ldd + x] = pp_pool4(src + p * (long)Hs * lds, lds, y, x);
+}
+
+// RAFT/corr.py:25-27: levels 1..3 from level 0 (level 0 is written by pp_corr_build)
+extern "C" int pp_corr_pool_pyramid(float* const* levels, long planes, int h, int w, cudaStream_t stream) {
+  int hs = h, ws = w;
+  for (int l = 1; l < 4; ++l) {
+    int hd = hs / 2, wd = ws / 2;
+    if (hd < 2 || wd < 2) return PP_ERR_SHAPE;        // the reference divides by (size-1): NaN below 2
+    long n = planes * hd * wd;
+    k_corr_pool<<<pp_blocks(n, 256), 256, 0, stream>>>(levels[l - 1], levels[l], planes, hs, pp_corr_ld(ws), hd, wd,
+                                                        pp_corr_ld(wd));
+    hs = hd; ws = wd;
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+struct PPLevels { const float* p[4]; };
+
+// One warp per source pixel: 4 levels x 81 taps; each lane walks taps lane, lane+32, ... so that the
+// 324 results of a pixel are written as one contiguous 1296-byte run (pixel-major output feeds the
+// 1x1 motion-encoder conv directly).  The per-pixel planes (<= 6.7 KB + 1.7 + 0.4 + 0.1) stay in L1.
+__global__ void __launch_bounds__(256) k_corr_lookup(PPLevels lv, const float* __restrict__ coords,
+                                                     float* __restrict__ out, long npix, int h, int w) {
+  const int lane = threadIdx.x & 31;
+  const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const float cx = coords[2 * pix], cy = coords[2 * pix + 1];
+  float* o = out + pix * 324;
+  int hl = h, wl = w;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int ld = pp_corr_ld(wl);
+    const float* plane = lv.p[l] + pix * (long)hl * ld;
+    for (int tap = lane; tap < 81; tap += 32)
+      o[l * 81 + tap] = pp_corr_tap(plane, hl, wl, ld, cx, cy, l, tap / 9, tap % 9);
+    hl >>= 1; wl >>= 1;
+  }
+}
+
+// replaces CorrBlock.__call__ (RAFT/corr.py:29-50): coords [B*h*w][2] -> out [B*h*w][324]
+extern "C" int pp_corr_lookup(const float* const* levels, const float* coords, float* out, long n_pairs, int h,
+                              int w, cudaStream_t stream) {
+  if ((h >> 3) < 2 || (w >> 3) < 2) return PP_ERR_SHAPE;
+  PPLevels lv;
+  for (int l = 0; l < 4; ++l) lv.p[l] = levels[l];
+  const long npix = n_pairs * h * w;
+  k_corr_lookup<<<pp_blocks(npix, 8), 256, 0, stream>>>(lv, coords, out, npix, h, w);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+__global__ void __launch_bounds__(256) k_convex_up(const float* __restrict__ mask, int ld_mask, float mask_scale,
+    const float* __restrict__ flow_lr, float* __restrict__ out, int n, int h, int w) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over n*h*w*64, sub-pixel fastest
+  long total = (long)n * h * w * 64;
+  if (i >= total) return;
+  int sub = (int)(i & 63); long px = i >> 6;
+  int b = (int)(px / ((long)h * w)); int r = (int)(px - (long)b * h * w); int y = r / w, x = r - y * w;
+  int si = sub >> 3, sj = sub & 7;
+  float2 v = pp_convex_up(mask + px * ld_mask, mask_scale, flow_lr + (long)b * h * w * 2, h, w, y, x, si, sj);
+  const long H = 8L * h, W = 8L * w;
+  float* ob = out + (long)b * 2 * H * W + (8L * y + si) * W + 8L * x + sj;
+  ob[0] = v.x; ob[H * W] = v.y;
+}
+
+// replaces RAFT.upsample_flow (RAFT/raft.py:73-84); mask_scale folds update.py:135's 0.25
+extern "C" int pp_convex_upsample(const float* mask, int ld_mask, float mask_scale, const float* flow_lr, float* out,
+                                  int n, int h, int w, cudaStream_t stream) {
+  if (ld_mask < 576) return PP_ERR_SHAPE;
+  long total = (long)n * h * w * 64;
+  k_convex_up<<<pp_blocks(total, 256), 256, 0, stream>>>(mask, ld_mask, mask_scale, flow_lr, out, n, h, w);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ generator input preparation
+__global__ void __launch_bounds__(256) k_gen_prep(const float* __restrict__ flows_f, const float* __restrict__ flows_b,
+    const float* __restrict__ masks_in, const float* __restrict__ masks_upd, float* __restrict__ dsf,
+    float* __restrict__ dsb, float* __restrict__ pmask, int lt, int H, int W) {
+  const int h = H / 4, w = W / 4;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long per = (long)h * w;
+  if (i >= (long)lt * per) return;
+  int f = (int)(i / per); int r = (int)(i - (long)f * per); int y = r / w, x = r - y * w;
+  const long HW = (long)H * W;
+  if (f < lt - 1) {
+    const float* pf = flows_f + (long)f * 2 * HW; const float* pb = flows_b + (long)f * 2 * HW;
+    dsf[2 * i] = pp_flow_ds4(pf, W, y, x); dsf[2 * i + 1] = pp_flow_ds4(pf + HW, W, y, x);
+    dsb[2 * i] = pp_flow_ds4(pb, W, y, x); dsb[2 * i + 1] = pp_flow_ds4(pb + HW, W, y, x);
+  }
+  pmask[2 * i] = masks_in[(long)f * HW + (long)(4 * y) * W + 4 * x];          // 'nearest' 1/4: element [4i,4j]
+  pmask[2 * i + 1] = masks_upd[(long)f * HW + (long)(4 * y) * W + 4 * x];
+}
+
+// replaces the F.interpolate block of InpaintGenerator.forward (model/propainter.py:338-342, :352)
+extern "C" int pp_gen_prep(const float* flows_f, const float* flows_b, const float* masks_in, const float* masks_upd,
+                           float* dsf, float* dsb, float* pmask, int lt, int H, int W, cudaStream_t stream) {
+  if (H % 4 || W % 4 || lt < 1) return PP_ERR_SHAPE;
+  long n = (long)lt * (H / 4) * (W / 4);
+  k_gen_prep<<<pp_blocks(n, 256), 256, 0, stream>>>(flows_f, flows_b, masks_in, masks_upd, dsf, dsb, pmask, lt, H, W);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// window flag = any(local frame) any(token in window) any(7x7/s3/p3 patch pixel) of the 1/4-res input mask
+__global__ void __launch_bounds__(128) k_window_mask(const float* __restrict__ pmask, int lt, int h, int w, int fh,
+                                                     int fw, int nww, int* __restrict__ flags) {
+  const int win = blockIdx.x;
+  const int wy = win / nww, wx = win - wy * nww;
+  int hit = 0;
+  const int per = 5 * 9 * 49;
+  for (int i = threadIdx.x; i < lt * per; i += blockDim.x) {
+    int f = i / per, r = i - f * per;
+    int tok = r / 49, tap = r - tok * 49;
+    int ty = wy * 5 + tok / 9, tx = wx * 9 + tok % 9;
+    if (ty >= fh || tx >= fw) continue;                    // zero padding of the token grid (:168-170)
+    int y = 3 * ty - 3 + tap / 7, x = 3 * tx - 3 + tap % 7;
+    if (y < 0 || y >= h || x < 0 || x >= w) continue;
+    if (pmask[2 * ((long)f * h * w + (long)y * w + x)] > 0.f) hit = 1;
+  }
+  hit = __syncthreads_or(hit);
+  if (threadIdx.x == 0) flags[win] = hit;
+}
+
+// replaces max_pool (propainter.py:349-350) + SparseWindowAttention's window max-pool/sum (:224-229)
+extern "C" int pp_window_mask(const float* pmask, int lt, int h, int w, int fh, int fw, int nwh, int nww, int* flags,
+                              cudaStream_t stream) {
+  k_window_mask<<<nwh * nww, 128, 0, stream>>>(pmask, lt, h, w, fh, fw, nww, flags);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ fusion feed-forward overlap-add
+__global__ void __launch_bounds__(256) k_ffn_fold(const float* __restrict__ Y, int ldy, int CH, int fh, int fw, int h,
+                                                  int w, int frames, float* __restrict__ F) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over frames*h*w*CH, channel fastest
+  long total = (long)frames * h * w * CH;
+  if (i >= total) return;
+  int c = (int)(i % CH); long px = i / CH;
+  int f = (int)(px / ((long)h * w)); int r = (int)(px - (long)f * h * w); int y = r / w, x = r - y * w;
+  F[i] = pp_ffn_fold(Y + (long)f * fh * fw * ldy, ldy, CH, fh, fw, y, x, c);
+}
+__global__ void __launch_bounds__(256) k_ffn_unfold_gelu(const float* __restrict__ F, int CH, int fh, int fw, int h,
+                                                         int w, int frames, float* __restrict__ Z, int ldz) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over tokens*49*CH, channel fastest
+  long total = (long)frames * fh * fw * 49 * CH;
+  if (i >= total) return;
+  int c = (int)(i % CH); long r = i / CH; int tap = (int)(r % 49); long tok = r / 49;
+  int f = (int)(tok / ((long)fh * fw)); int tr = (int)(tok - (long)f * fh * fw); int ty = tr / fw, tx = tr - ty * fw;
+  int y = 3 * ty - 3 + tap / 7, x = 3 * tx - 3 + tap % 7;
+  float v = 0.f;
+  if (y >= 0 && y < h && x >= 0 && x < w) v = pp_gelu(F[(((long)f * h + y) * w + x) * CH + c]);
+  Z[tok * ldz + tap * CH + c] = v;
+}
+
+extern "C" size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH) {
+  return (size_t)frames * h * w * CH * sizeof(float);
+}
+// replaces fold -> /normalizer -> unfold -> GELU of FusionFeedForward.forward
+// (model/modules/sparse_transformer.py:81-100).  Y,Z: [frames*fh*fw][ld], columns tap-major (tap*CH+c).
+extern "C" int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH,
+                                  void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const int fh = (h - 1) / 3 + 1, fw = (w - 1) / 3 + 1;
+  if (ldy < 49 * CH || ldz < 49 * CH) return PP_ERR_SHAPE;
+  if (ws_bytes < pp_ffn_overlap_add_workspace_bytes(frames, h, w, CH)) return PP_ERR_WORKSPACE;
+  float* F = (float*)workspace;
+  long n1 = (long)frames * h * w * CH, n2 = (long)frames * fh * fw * 49 * CH;
+  k_ffn_fold<<<pp_blocks(n1, 256), 256, 0, stream>>>(Y, ldy, CH, fh, fw, h, w, frames, F);
+  k_ffn_unfold_gelu<<<pp_blocks(n2, 256), 256, 0, stream>>>(F, CH, fh, fw, h, w, frames, Z, ldz);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ frame conversion + compositing
+__global__ void __launch_bounds__(256) k_u8_to_frames(const uint8_t* __restrict__ src, float* __restrict__ dst, int T,
+                                                      int H, int W) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over T*3*H*W (planar output order)
+  long HW = (long)H * W;
+  if (i >= (long)T * 3 * HW) return;
+  long f = i / (3 * HW); long r = i - f * 3 * HW; int c = (int)(r / HW); long p = r - (long)c * HW;
+  float v = PP_DIV((float)src[(f * HW + p) * 3 + c], 255.0f);
+  dst[i] = PP_SUB(PP_MUL(v, 2.0f), 1.0f);
+}
+// replaces to_tensors()(frames)*2-1 (core/utils.py:130-170, inference_propainter.py:264)
+extern "C" int pp_u8_to_frames(const uint8_t* src, float* dst, int T, int H, int W, cudaStream_t stream) {
+  long n = (long)T * 3 * H * W;
+  k_u8_to_frames<<<pp_blocks(n, 256), 256, 0, stream>>>(src, dst, T, H, W);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+__global__ void __launch_bounds__(256) k_composite(const float* __restrict__ pred, const float* __restrict__ masks,
+    const uint8_t* __restrict__ ori, uint8_t* __restrict__ comp, PPWindowIds ids, int H, int W) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over n*H*W*3 (HWC order of the uint8 output)
+  long HW = (long)H * W;
+  if (i >= (long)ids.n * HW * 3) return;
+  int k = (int)(i / (HW * 3)); long r = i - (long)k * HW * 3; long p = r / 3; int c = (int)(r - p * 3);
+  int idx = ids.frame[k];
+  long o = ((long)idx * HW + p) * 3 + c;
+  comp[o] = pp_composite(pred[((long)k * 3 + c) * HW + p], masks[(long)idx * HW + p], ori[o], comp[o], ids.first[k]);
+}
+// replaces the numpy compositing / blending of inference_propainter.py:437-450 (no device->host sync)
+extern "C" int pp_composite_blend_u8(const float* pred, const float* masks, const uint8_t* ori, uint8_t* comp,
+                                     const PPWindowIds* ids, int H, int W, cudaStream_t stream) {
+  if (ids->n < 1 || ids->n > PP_MAX_WINDOW) return PP_ERR_SHAPE;
+  long n = (long)ids->n * H * W * 3;
+  k_composite<<<pp_blocks(n, 256), 256, 0, stream>>>(pred, masks, ori, comp, *ids, H, W);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}

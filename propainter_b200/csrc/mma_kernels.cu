@@ -1,0 +1,351 @@
+// Tensor-core kernels of the ProPainter hot path, first generation: warp-level TF32 mma.sync tiles.
+//   * pp_corr_build        RAFT all-pairs correlation (3xTF32 split => fp32-accurate), level-0 writer
+//   * pp_deform_align      modulated deformable 3x3 alignment: offset prep + bilinear gather + GEMM fused
+//   * pp_sparse_window_attn mask-guided sparse window attention, flash-style, K/V gathered arithmetically
+#include "pp_elem.cuh"
+#include "pp_mma.cuh"
+#include "../../include/propainter_b200.h"
+
+#define PP_LAUNCH_CHECK() do { if (cudaPeekAtLastError() != cudaSuccess) return PP_ERR_LAUNCH; } while (0)
+
+// ================================================================ RAFT correlation volume (level 0)
+// C[i][j] = <f1[i,:], f2[j,:]> / sqrt(D)  (RAFT/corr.py:52-60).  fmaps pixel-major [frame][h*w][D].
+// 64x64x32 tiles, 4 warps (2x2) of 32x32; fp32 accuracy kept with the 3xTF32 split
+// (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) because the reference computes this matmul in full fp32.
+__global__ void __launch_bounds__(128) k_corr_build(const float* __restrict__ fmap, int D, const int* __restrict__ idx1,
+    const int* __restrict__ idx2, float* __restrict__ lvl0, int h, int w, int ld0, float scale) {
+  __shared__ __align__(16) float As[64][36];
+  __shared__ __align__(16) float Bs[64][36];
+  const int N = h * w;
+  const int pair = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const float* A = fmap + (long)idx1[pair] * N * D;
+  const float* B = fmap + (long)idx2[pair] * N * D;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int idx = tid + 128 * r, row = idx >> 3, c4 = idx & 7;
+      int ia = min(i0 + row, N - 1), jb = min(j0 + row, N - 1);
+      pp_cp_async16(&As[row][c4 * 4], A + (long)ia * D + k0 + c4 * 4);
+      pp_cp_async16(&Bs[row][c4 * 4], B + (long)jb * D + k0 + c4 * 4);
+    }
+    pp_cp_async_commit();
+    pp_cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = wm * 32 + mt * 16 + g;
+        float v[4] = {As[r0][ks * 8 + t], As[r0 + 8][ks * 8 + t], As[r0][ks * 8 + t + 4], As[r0 + 8][ks * 8 + t + 4]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ah[mt][q] = pp_tf32(v[q]); al[mt][q] = pp_tf32(v[q] - __uint_as_float(ah[mt][q])); }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c0 = wn * 32 + nt * 8 + g;
+        float v[2] = {Bs[c0][ks * 8 + t], Bs[c0][ks * 8 + t + 4]};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { bh[nt][q] = pp_tf32(v[q]); bl[nt][q] = pp_tf32(v[q] - __uint_as_float(bh[nt][q])); }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          pp_mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+          pp_mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+          pp_mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+  }
+  const long plane = (long)h * ld0;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int i = i0 + wm * 32 + mt * 16 + g + ((q & 2) ? 8 : 0);
+        int j = j0 + wn * 32 + nt * 8 + 2 * t + (q & 1);
+        if (i < N && j < N) {
+          int y2 = j / w, x2 = j - y2 * w;
+          lvl0[((long)pair * N + i) * plane + (long)y2 * ld0 + x2] = acc[mt][nt][q] * scale;
+        }
+      }
+}
+
+// replaces CorrBlock.corr (RAFT/corr.py:52-60); pooled levels come from pp_corr_pool_pyramid
+extern "C" int pp_corr_build(const float* fmap, int D, const int* idx1, const int* idx2, int n_pairs, float* lvl0,
+                             int h, int w, cudaStream_t stream) {
+  if (D % 32 || n_pairs < 1) return PP_ERR_SHAPE;
+  const int N = h * w;
+  dim3 grid((N + 63) / 64, (N + 63) / 64, n_pairs);
+  k_corr_build<<<grid, 128, 0, stream>>>(fmap, D, idx1, idx2, lvl0, h, w, pp_corr_ld(w), 1.0f / sqrtf((float)D));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ deformable alignment
+// out[p][n] = bias[n] + sum_{k<9,c<Cin} Wp[k*Cin+c][n] * sample(x, p, k, c)            (TF32 MMA)
+// CTA = 32 pixels x 128 outputs, 4 warps (2 along M x 2 along N).  Each K-step stages the modulated
+// bilinear samples of (tap k, 32 channels) for the 32 pixels into shared memory -- the im2col matrix
+// torchvision materialises in HBM never exists -- and the matching 32x128 weight slab via cp.async.
+__global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float* __restrict__ o,
+    int ld_o, const float* __restrict__ flow, float max_res, const float* __restrict__ Wp,
+    const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin) {
+  __shared__ __align__(16) float As[32][36];
+  __shared__ __align__(16) float Bs[32][136];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int px_l = tid >> 2, cseg = tid & 3;
+  const long npix = (long)H * W;
+  const long pix = (long)blockIdx.x * 32 + px_l;
+  const bool valid = pix < npix;
+  const int y = valid ? (int)(pix / W) : 0, xx = valid ? (int)(pix - (long)y * W) : 0;
+  const int cpg = Cin / 16;
+  const float* op = o + (valid ? pix : 0) * ld_o;
+  const float* fp = flow ? flow + 2 * (valid ? pix : 0) : nullptr;
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  for (int k = 0; k < 9; ++k) {
+    for (int c0 = 0; c0 < Cin; c0 += 32) {
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
+        pp_cp_async16(&Bs[row][c4 * 4], Wp + ((long)k * Cin + c0 + row) * 128 + c4 * 4);
+      }
+      pp_cp_async_commit();
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+      if (valid) {
+        const int c = c0 + cseg * 8;
+        PPDTap tp = pp_deform_tap(op, fp, max_res, c / cpg, k, y, xx);
+        PPDW d = pp_deform_weights(tp, H, W);
+        const float* p = x + ((long)d.y0 * W + d.x0) * ld_x + c;
+#define PP_DACC(ptr, wt)                                                                         \
+  if ((wt) != 0.f) { const float4 u = *reinterpret_cast<const float4*>(ptr);                    \
+    const float4 v = *reinterpret_cast<const float4*>((ptr) + 4);                               \
+    s0.x += u.x * (wt); s0.y += u.y * (wt); s0.z += u.z * (wt); s0.w += u.w * (wt);             \
+    s1.x += v.x * (wt); s1.y += v.y * (wt); s1.z += v.z * (wt); s1.w += v.w * (wt); }
+        PP_DACC(p, d.w00)
+        PP_DACC(p + ld_x, d.w01)
+        PP_DACC(p + (long)W * ld_x, d.w10)
+        PP_DACC(p + (long)W * ld_x + ld_x, d.w11)
+#undef PP_DACC
+      }
+      *reinterpret_cast<float4*>(&As[px_l][cseg * 8]) = s0;
+      *reinterpret_cast<float4*>(&As[px_l][cseg * 8 + 4]) = s1;
+      pp_cp_async_wait<0>();
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        const int r0 = wm * 16 + g;
+        a[0] = pp_tf32(As[r0][ks * 8 + t]); a[1] = pp_tf32(As[r0 + 8][ks * 8 + t]);
+        a[2] = pp_tf32(As[r0][ks * 8 + t + 4]); a[3] = pp_tf32(As[r0 + 8][ks * 8 + t + 4]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t b[2];
+          const int n = wn * 64 + nt * 8 + g;
+          b[0] = pp_tf32(Bs[ks * 8 + t][n]); b[1] = pp_tf32(Bs[ks * 8 + t + 4][n]);
+          pp_mma_tf32(acc[nt], a, b);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int n = wn * 64 + nt * 8 + 2 * t;
+    const float b0 = bias[n], b1 = bias[n + 1];
+    const long p0 = (long)blockIdx.x * 32 + wm * 16 + g, p1 = p0 + 8;
+    if (p0 < npix) { float2 v; v.x = acc[nt][0] + b0; v.y = acc[nt][1] + b1; *reinterpret_cast<float2*>(out + p0 * ld_out + n) = v; }
+    if (p1 < npix) { float2 v; v.x = acc[nt][2] + b0; v.y = acc[nt][3] + b1; *reinterpret_cast<float2*>(out + p1 * ld_out + n) = v; }
+  }
+}
+
+// replaces DeformableAlignment.forward / SecondOrderDeformableAlignment.forward after the offset-net
+// convs (model/propainter.py:57-69, model/recurrent_flow_completion.py:31-44 -> torchvision deform_conv2d)
+extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
+                               const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin,
+                               int Cout, cudaStream_t stream) {
+  if (Cout != 128 || Cin % 32 || (Cin / 16) % 8) return PP_ERR_SHAPE;
+  if (ld_x % 4 || ld_out % 2 || ld_o < 432) return PP_ERR_ALIGN;
+  const long npix = (long)H * W;
+  k_deform_align<<<(int)((npix + 31) / 32), 128, 0, stream>>>(x, ld_x, o, ld_o, flow, max_res, w_packed, bias, out,
+                                                             ld_out, H, W, Cin);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ sparse window attention
+// sparse_transformer.py:158-281.  One CTA = 64 query rows of one (window, head); flash-style online
+// softmax over key tiles of 64.  Keys of a masked window, per key frame: 45 own + 148 rolled (token
+// table) + pooled tokens; unmasked windows attend per frame to their own 45 tokens.  Nothing is
+// materialised: K/V rows (512 B per head) are gathered with cp.async straight from the QKV buffer.
+#define AT_LD 132
+template <bool MASKED>
+__global__ void __launch_bounds__(128) k_sparse_attn(PPAttnParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float (*Ks)[AT_LD] = reinterpret_cast<float (*)[AT_LD]>(smem);
+  float (*Vs)[AT_LD] = reinterpret_cast<float (*)[AT_LD]>(smem + 64 * AT_LD);
+  const int win = blockIdx.z, head = blockIdx.y;
+  if (MASKED != (p.flags[win] != 0)) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int* ktab = p.key_tok + (long)win * p.NKO;
+  const int hoff = head * 128;
+  const int q0 = MASKED ? blockIdx.x * 64 : blockIdx.x * p.WN;
+  const int nq = MASKED ? min(64, p.t * p.WN - q0) : p.WN;
+  const int keys_per_frame = p.NKO + p.NP;
+  const int nkeys = MASKED ? p.nkf * keys_per_frame : p.WN;
+
+  // ---- stage the query tile through Ks, pre-scaled into the log2 domain
+  for (int r = 0; r < 16; ++r) {
+    int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nq) {
+      int qi = q0 + row, fr = qi / p.WN, tok = ktab[qi - fr * p.WN];
+      v = *reinterpret_cast<const float4*>(p.qkv + ((long)fr * p.NT + tok) * p.ld_qkv + hoff + c4 * 4);
+    }
+    v.x *= p.scale_log2; v.y *= p.scale_log2; v.z *= p.scale_log2; v.w *= p.scale_log2;
+    *reinterpret_cast<float4*>(&Ks[row][c4 * 4]) = v;
+  }
+  __syncthreads();
+  uint32_t qa[16][4];
+  {
+    const int r0 = warp * 16 + g;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      qa[ks][0] = pp_tf32(Ks[r0][ks * 8 + t]); qa[ks][1] = pp_tf32(Ks[r0 + 8][ks * 8 + t]);
+      qa[ks][2] = pp_tf32(Ks[r0][ks * 8 + t + 4]); qa[ks][3] = pp_tf32(Ks[r0 + 8][ks * 8 + t + 4]);
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float oacc[16][4];
+#pragma unroll
+  for (int a = 0; a < 16; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) oacc[a][b] = 0.f;
+
+  for (int kt0 = 0; kt0 < nkeys; kt0 += 64) {
+    __syncthreads();
+    // ---- gather 64 keys x 128 dims of K and V
+    for (int r = 0; r < 16; ++r) {
+      int idx = tid + 128 * r, key = idx >> 5, c4 = idx & 31;
+      int j = kt0 + key;
+      if (j < nkeys) {
+        const float* src;
+        if (MASKED) {
+          int kfi = j / keys_per_frame, slot = j - kfi * keys_per_frame;
+          int fr = p.kf_start + kfi * p.kf_step;
+          if (slot < p.NKO) src = p.qkv + ((long)fr * p.NT + ktab[slot]) * p.ld_qkv + p.C + hoff;
+          else src = p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + hoff;          // pool rows: K at 0, V at C
+        } else {
+          src = p.qkv + ((long)blockIdx.x * p.NT + ktab[j]) * p.ld_qkv + p.C + hoff;
+        }
+        pp_cp_async16(&Ks[key][c4 * 4], src + c4 * 4);
+        pp_cp_async16(&Vs[key][c4 * 4], src + p.C + c4 * 4);
+      } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&Ks[key][c4 * 4]) = z;
+        *reinterpret_cast<float4*>(&Vs[key][c4 * 4]) = z;
+      }
+    }
+    pp_cp_async_commit();
+    pp_cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- S = Q K^T (already scaled, log2 domain)
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        uint32_t b[2];
+        b[0] = pp_tf32(Ks[nt * 8 + g][ks * 8 + t]); b[1] = pp_tf32(Ks[nt * 8 + g][ks * 8 + t + 4]);
+        pp_mma_tf32(s[nt], qa[ks], b);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      int j = kt0 + nt * 8 + 2 * t;
+      if (j >= nkeys) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (j + 1 >= nkeys) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+      rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { oacc[nt][0] *= al0; oacc[nt][1] *= al0; oacc[nt][2] *= al1; oacc[nt][3] *= al1; }
+
+    // ---- O += P V.  P's C-fragment is reused as the A-fragment by renaming the k index inside each
+    // 8-key group (k=t <-> key 2t, k=t+4 <-> key 2t+1); V rows are fetched with the same renaming.
+#pragma unroll
+    for (int kg = 0; kg < 8; ++kg) {
+      uint32_t a[4] = {pp_tf32(s[kg][0]), pp_tf32(s[kg][2]), pp_tf32(s[kg][1]), pp_tf32(s[kg][3])};
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        uint32_t b[2];
+        b[0] = pp_tf32(Vs[kg * 8 + 2 * t][nt * 8 + g]); b[1] = pp_tf32(Vs[kg * 8 + 2 * t + 1][nt * 8 + g]);
+        pp_mma_tf32(oacc[nt], a, b);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  const int ra = warp * 16 + g, rb = ra + 8;
+  float* oa = nullptr; float* ob = nullptr;
+  if (ra < nq) { int qi = q0 + ra, fr = qi / p.WN; oa = p.out + ((long)fr * p.NT + ktab[qi - fr * p.WN]) * p.ld_out + hoff; }
+  if (rb < nq) { int qi = q0 + rb, fr = qi / p.WN; ob = p.out + ((long)fr * p.NT + ktab[qi - fr * p.WN]) * p.ld_out + hoff; }
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    if (oa) { float2 v; v.x = oacc[nt][0] * inv0; v.y = oacc[nt][1] * inv0; *reinterpret_cast<float2*>(oa + nt * 8 + 2 * t) = v; }
+    if (ob) { float2 v; v.x = oacc[nt][2] * inv1; v.y = oacc[nt][3] * inv1; *reinterpret_cast<float2*>(ob + nt * 8 + 2 * t) = v; }
+  }
+}
+
+// replaces SparseWindowAttention.forward between the q/k/v Linear layers and `proj`
+// (model/modules/sparse_transformer.py:177-275)
+extern "C" int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream) {
+  const PPAttnParams& p = *prm;
+  if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 2) return PP_ERR_SHAPE;
+  const int smem = 2 * 64 * AT_LD * (int)sizeof(float);
+  if (cudaFuncSetAttribute(k_sparse_attn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sparse_attn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return PP_ERR_LAUNCH;
+  const int heads = p.C / 128;
+  dim3 gm((p.t * p.WN + 63) / 64, heads, n_windows), gu(p.t, heads, n_windows);
+  k_sparse_attn<true><<<gm, 128, smem, stream>>>(p);
+  k_sparse_attn<false><<<gu, 128, smem, stream>>>(p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
