@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the ProPainter inference hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1] [--no-cpu-baseline]
+
+A "step" is one full pass of stages 1-4 (RAFT flow -> flow completion -> image propagation ->
+sliding-window generator + compositing) over one synthetic clip.  N=1 workload = BASELINE.json
+configs[1]: 80 frames, 432x240, object-removal mask, fp32, neighbor_length=10, ref_stride=10,
+subvideo_length=80, raft_iter=20, random-init weights.
+  value : frames/s with the uint8 clip + masks already resident in HBM
+  e2e   : frames/s through ProPainterPipeline.__call__ with pinned HOST buffers: H2D of the clip
+          and masks and D2H of the composited uint8 video inside the timed region
+N>1: one clip per rank (clips are independent units; weak scaling, no data-path collective).
+--impl reference: the oracle (CPU restatement of the reference's PyTorch path) on the host cores
+over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "inpainted frames/sec at 432x240x80f"
+WORKLOADS = {
+    "c2": dict(T=80, H=240, W=432, mask="ellipse", raft_iter=20,
+               name="C2: 80-frame 432x240 object-removal, neighbor_length=10 ref_stride=10 subvideo_length=80, fp32"),
+    "c1": dict(T=8, H=128, W=128, mask="square", raft_iter=20, name="C1: 8-frame 128x128 square mask, fp32"),
+}
+CPU_SAMPLE_FRAMES = 6      # bounded sample of the same workload for the CPU arm (full clip ~ 10 min of CPU)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def run_reference(args, wl):
+    """CPU arm: the oracle on the host cores over a bounded sample (first CPU_SAMPLE_FRAMES frames)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pipeline_ref
+    from propainter_b200 import schemas, synth
+    from propainter_b200._params import ParamNet
+    T = min(CPU_SAMPLE_FRAMES, wl["T"])
+    u8, fm, md = synth.make_clip(T, wl["H"], wl["W"], mask=wl["mask"], seed=0)
+    sds = {"raft": ParamNet(schemas.raft_schema(), seed=1).state_dict(), "rfc": ParamNet(schemas.rfc_schema(), seed=2).state_dict(),
+           "gen": ParamNet(schemas.generator_schema(), seed=3).state_dict()}
+    cores = torch.get_num_threads()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pipeline_ref.run_pipeline(sds, u8, fm, md, raft_iter=wl["raft_iter"])
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    val = T * len(times) / tot
+    sample = f"first {T} frames of the workload clip ({wl['H']}x{wl['W']}), full 4-stage pipeline, raft_iter={wl['raft_iter']}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(wl, budget_s=40.0):
+    import torch
+    from oracle import pipeline_ref
+    from propainter_b200 import schemas, synth
+    from propainter_b200._params import ParamNet
+    T = min(CPU_SAMPLE_FRAMES, wl["T"])
+    u8, fm, md = synth.make_clip(T, wl["H"], wl["W"], mask=wl["mask"], seed=0)
+    sds = {"raft": ParamNet(schemas.raft_schema(), seed=1).state_dict(), "rfc": ParamNet(schemas.rfc_schema(), seed=2).state_dict(),
+           "gen": ParamNet(schemas.generator_schema(), seed=3).state_dict()}
+    t0 = time.perf_counter()
+    pipeline_ref.run_pipeline(sds, u8, fm, md, raft_iter=wl["raft_iter"])
+    dt = time.perf_counter() - t0
+    return {"value": T / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {T} frames of the workload clip, full 4-stage pipeline once ({dt:.1f} s)"}
+
+
+def roofline_probe(torch, pipe, wl):
+    """Dominant own kernel measured live with CUDA events on the launch stream."""
+    from propainter_b200 import ops
+    hbm, tf, src = peaks()
+    h, w = wl["H"] // 8, wl["W"] // 8
+    B = 22 if wl["W"] <= 640 else 6                           # pairs per RAFT refinement batch (2*(clip-1))
+    dev = pipe.device
+    fmap = torch.randn(B // 2 + 1, h * w, 256, device=dev)
+    a = torch.arange(B // 2, device=dev, dtype=torch.int32)
+    levels = ops.corr_alloc(B, h, w, dev)
+    ops.corr_build(fmap, torch.cat([a, a + 1]), torch.cat([a + 1, a]), levels, h, w)
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+    coords = (torch.stack([xs, ys], -1).float()[None] + torch.randn(B, h, w, 2, device=dev) * 3).contiguous()
+    out = torch.empty(B, h, w, 324, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    for _ in range(3):
+        ops.corr_lookup(levels, coords, out)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.corr_lookup(levels, coords, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.mean(ts)
+    # algorithmic bytes per pair-iteration: unique 10x10 patches at 4 levels + the 324-ch output
+    npx = h * w
+    alg = B * (npx * 4 * 100 * 4 + npx * 324 * 4 + npx * 8)
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"kernel": "k_corr_lookup", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "traffic": None, "peak_source": src, "launch_ms": ms, "algorithmic_bytes": alg}
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.barrier()
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    from propainter_b200 import ops, synth
+    from propainter_b200.inference_propainter import InferenceConfig, ProPainterPipeline
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    u8_np, fm, md = synth.make_clip(wl["T"], wl["H"], wl["W"], mask=wl["mask"], seed=rank)
+    u8_host = torch.from_numpy(u8_np).pin_memory()
+    fm_host, md_host = fm.pin_memory(), md.pin_memory()
+    out_host = torch.empty_like(u8_host).pin_memory()
+    pipe = ProPainterPipeline(device=dev)
+    cfg = InferenceConfig(raft_iter=wl["raft_iter"])
+    u8_dev, fm_dev, md_dev = u8_host.to(dev), fm_host.to(dev), md_host.to(dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)          # 256 MiB > 126 MB L2
+
+    def step_resident():
+        return pipe(u8_dev, fm_dev, md_dev, cfg)
+
+    def step_e2e():
+        comp = pipe(u8_host, fm_host, md_host, cfg)            # H2D inside
+        out_host.copy_(comp, non_blocking=True)                # D2H of the result
+        return comp
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = ops.LAUNCHES
+        total = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), ops.LAUNCHES - l0, clocks
+
+    ms_total, launches, clocks = timed(step_resident, args.steps, args.warmup, True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    frames_total = wl["T"] * world * args.steps
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": frames_total / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core products, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_step_per_gpu": wl["T"], "parallelism": f"clip-parallel x{world}",
+                       "weights": "random-init (seeded)", "l2": "256 MiB flush between timed steps"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": u8_host.numel() + 4 * (fm_host.numel() + md_host.numel()),
+                    "d2h_bytes_per_step": out_host.numel()},
+        }
+        try:
+            line["roofline"] = roofline_probe(torch, pipe, wl)
+        except Exception as exc:                                   # never lose the headline line to the probe
+            line["roofline"] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

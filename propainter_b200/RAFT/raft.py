@@ -1,0 +1,143 @@
+"""RAFT optical flow (basic model) on the B200 hot path.
+
+Drop-in for the reference's ``RAFT`` (RAFT/raft.py:24-146): same constructor argument, same
+``forward(image1, image2, iters, flow_init, test_mode)`` result in test mode, same state_dict.
+What differs is the execution plan:
+  * features live pixel-major (channels-last); convs are cuDNN through torch
+  * the all-pairs volume + pyramid (corr.py:13-27) is built by ``ops.corr_build`` (fp32-accurate
+    3xTF32 tensor-core GEMM) into row-padded planes; the 4-level 9x9 lookup (corr.py:29-50) is one
+    kernel writing the 324-channel pixel-major tensor the motion encoder consumes
+  * z and r gates of the SepConvGRU share one conv (concatenated weights); eval BatchNorm is folded
+    into the cnet convs; the mask head + convex upsampling run only on the last iteration (the
+    reference computes them 20x and keeps one, raft.py:135-146)
+  * ``flows_bidirectional`` encodes every frame once for both directions (the reference encodes each
+    frame up to 4x, flow_comp_raft.py:48-49); per-sample InstanceNorm makes this exactly equivalent
+"""
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from .._params import ParamNet
+from ..nn_util import as_nchw, as_pm, cl, conv
+from ..schemas import raft_schema
+
+
+class RAFT(ParamNet):
+    hidden_dim = 128
+    context_dim = 128
+
+    def __init__(self, args=None, seed=None):
+        if args is not None and getattr(args, "small", False):
+            raise NotImplementedError("only the basic RAFT model is on ProPainter's path (flow_comp_raft.py:15)")
+        super().__init__(raft_schema(), seed=seed)
+        self.args = args
+
+    # ------------------------------------------------------------------ weights
+    def _wb(self, key, bn=None):
+        """(weight, bias) of a conv, channels_last, with eval-BatchNorm `bn` folded in if given."""
+        def build():
+            w, b = self.P[key + ".weight"], self.P[key + ".bias"]
+            if bn is not None and (bn + ".running_var") in self.P:
+                s = self.P[bn + ".weight"] / torch.sqrt(self.P[bn + ".running_var"] + 1e-5)
+                w = w * s.view(-1, 1, 1, 1)
+                b = (b - self.P[bn + ".running_mean"]) * s + self.P[bn + ".bias"]
+            return cl(w), b.contiguous()
+        return self.packed("wb:" + key, build)
+
+    def _gates(self, tag):
+        def build():
+            u = "update_block.gru."
+            w = torch.cat([self.P[u + f"convz{tag}.weight"], self.P[u + f"convr{tag}.weight"]], 0)
+            b = torch.cat([self.P[u + f"convz{tag}.bias"], self.P[u + f"convr{tag}.bias"]], 0)
+            return cl(w), b.contiguous()
+        return self.packed("zr" + tag, build)
+
+    # ------------------------------------------------------------------ encoders (extractor.py:168-192)
+    def _encode(self, p, x):
+        inst = p == "fnet"
+
+        def cn(key, bn, t, stride=1, pad=1, relu=True):
+            y = conv(t, self._wb(key, None if inst else bn), stride, pad)
+            if inst:
+                y = F.instance_norm(y, eps=1e-5)
+            return F.relu_(y) if relu else y
+
+        x = cn(p + ".conv1", p + ".norm1", x, 2, 3)
+        for li, stride in ((1, 1), (2, 2), (3, 2)):
+            for bi in (0, 1):
+                q = f"{p}.layer{li}.{bi}"
+                s = stride if bi == 0 else 1
+                y = cn(q + ".conv1", q + ".norm1", x, s, 1)
+                y = cn(q + ".conv2", q + ".norm2", y, 1, 1)
+                if s != 1:
+                    x = cn(q + ".downsample.0", q + ".norm3", x, s, 0, relu=False)
+                x = F.relu_(x + y)
+        return conv(x, self._wb(p + ".conv2"))
+
+    def encode_frames(self, frames):
+        """frames [n,3,H,W] -> (fmap pixel-major [n, h*w, 256], net [n,128,h,w], inp [n,128,h,w])."""
+        x = frames.contiguous(memory_format=torch.channels_last)
+        fmap = as_pm(self._encode("fnet", x).float())
+        n, h, w, d = fmap.shape
+        c = self._encode("cnet", x)
+        net, inp = torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
+        return fmap.view(n, h * w, d), net, inp, (h, w)
+
+    # ------------------------------------------------------------------ refinement loop (raft.py:122-146)
+    def _refine(self, fmap, idx1, idx2, net, inp, hw, iters, flow_init=None):
+        h, w = hw
+        B = idx1.numel()
+        dev = fmap.device
+        levels = ops.corr_alloc(B, h, w, dev)
+        ops.corr_build(fmap, idx1, idx2, levels, h, w)
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+        c0 = torch.stack([xs, ys], -1).float()[None].expand(B, h, w, 2).contiguous()     # coords_grid (utils.py:74-77)
+        c1 = c0.clone()
+        if flow_init is not None:
+            c1 = c1 + as_pm(flow_init)
+        net = net.contiguous(memory_format=torch.channels_last)
+        inp = inp.contiguous(memory_format=torch.channels_last)
+        u = "update_block."
+        corr = torch.empty(B, h, w, 324, device=dev)
+        for _ in range(iters):
+            ops.corr_lookup(levels, c1, corr)
+            flow = as_nchw(c1 - c0)
+            cor = F.relu_(conv(as_nchw(corr), self._wb(u + "encoder.convc1")))
+            cor = F.relu_(conv(cor, self._wb(u + "encoder.convc2"), 1, 1))
+            flo = F.relu_(conv(flow, self._wb(u + "encoder.convf1"), 1, 3))
+            flo = F.relu_(conv(flo, self._wb(u + "encoder.convf2"), 1, 1))
+            mot = F.relu_(conv(torch.cat([cor, flo], 1), self._wb(u + "encoder.conv"), 1, 1))
+            x = torch.cat([inp, mot, flow], 1)
+            for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
+                hx = torch.cat([net, x], 1)
+                zr = torch.sigmoid_(conv(hx, self._gates(tag), 1, pad))
+                z, r = zr[:, :128], zr[:, 128:]
+                q = torch.tanh_(conv(torch.cat([r * net, x], 1), self._wb(u + f"gru.convq{tag}"), 1, pad))
+                net = torch.lerp(net, q, z)                     # (1-z)*h + z*q
+            d = conv(F.relu_(conv(net, self._wb(u + "flow_head.conv1"), 1, 1)), self._wb(u + "flow_head.conv2"), 1, 1)
+            c1 = c1 + as_pm(d)
+        flow_lr = c1 - c0
+        mask = conv(F.relu_(conv(net, self._wb(u + "mask.0"), 1, 1)), self._wb(u + "mask.2"))
+        up = ops.convex_upsample(as_pm(mask), flow_lr.contiguous(), 0.25)
+        return as_nchw(flow_lr), up
+
+    @torch.no_grad()
+    def forward(self, image1, image2, iters=12, flow_init=None, test_mode=True):
+        """raft.py:87-146.  image1/2 [N,3,H,W] in [-1,1] -> (flow_lowres [N,2,H/8,W/8], flow_up [N,2,H,W])."""
+        if not test_mode:
+            raise NotImplementedError("training-mode flow_predictions list is outside the inference hot path")
+        n = image1.shape[0]
+        fmap, net, inp, hw = self.encode_frames(torch.cat([image1, image2], 0))
+        idx1 = torch.arange(n, device=image1.device, dtype=torch.int32)
+        return self._refine(fmap, idx1, idx1 + n, net[:n], inp[:n], hw, iters, flow_init)
+
+    @torch.no_grad()
+    def flows_bidirectional(self, frames, iters=20):
+        """frames [l,3,H,W] -> (forward flows i->i+1, backward flows i+1->i), each [l-1,2,H,W]."""
+        l = frames.shape[0]
+        fmap, net, inp, hw = self.encode_frames(frames)
+        a = torch.arange(l - 1, device=frames.device, dtype=torch.int32)
+        idx1, idx2 = torch.cat([a, a + 1]), torch.cat([a + 1, a])
+        sel = idx1.long()
+        _, up = self._refine(fmap, idx1, idx2, net[sel], inp[sel], hw, iters)
+        return up[:l - 1], up[l - 1:]

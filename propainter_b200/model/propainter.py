@@ -1,0 +1,162 @@
+"""``InpaintGenerator``: image propagation, encoder, flow-guided deformable feature propagation,
+mask-guided sparse transformer, decoder -- B200 execution plan.
+
+Drop-in for the generator half of model/propainter.py (:256-372) of the reference: same constructor,
+``img_propagation`` / ``forward`` signatures and results, same state_dict (216 tensors).  The GAN
+discriminators (:378-532) are training-only and not part of the inference path.
+"""
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from .._params import ParamNet
+from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels
+from ..schemas import generator_schema
+from ..window_index import padded_grid, token_grid
+from .modules.sparse_transformer import WIN, TransformerExec
+
+
+def _lrelu(x, s=0.2):
+    return F.leaky_relu_(x, s)
+
+
+class InpaintGenerator(ParamNet):
+    def __init__(self, init_weights=True, model_path=None, seed=None):
+        # `init_weights` is kept for signature compatibility; a fresh net is always given a seeded
+        # synthetic init (the reference's N(0,0.02) init is a training detail, base_module.py:22-56).
+        super().__init__(generator_schema(), seed=seed)
+        self.tx = TransformerExec(self)
+        if model_path is not None:
+            print("Pretrained ProPainter has loaded...")
+            self.load_state_dict(torch.load(model_path, map_location="cpu"), strict=True)
+
+    # ------------------------------------------------------------------ packed weights
+    def _wb(self, key, cin_pad=None):
+        def build():
+            w = self.P[key + ".weight"]
+            if cin_pad is not None:
+                w = pad_in_channels(w, cin_pad)
+            return cl(w), self.P[key + ".bias"].contiguous()
+        return self.packed(f"wb:{key}:{cin_pad}", build)
+
+    def _dcn(self, name):
+        def build():
+            p = f"feat_prop_module.deform_align.{name}"
+            return ops.pack_deform_weight(self.P[p + ".weight"]), self.P[p + ".bias"].contiguous()
+        return self.packed("dcn:" + name, build)
+
+    # ------------------------------------------------------------------ image propagation
+    @torch.no_grad()
+    def img_propagation(self, masked_frames, completed_flows, masks, interpolation="nearest"):
+        """propainter.py:315-317 -> BidirectionalPropagation(3, learnable=False) :104-190, as one fused scan."""
+        if interpolation not in ("nearest", "bilinear"):
+            raise ValueError(f"unsupported interpolation {interpolation!r}")
+        if tuple(masked_frames.shape[-2:]) != tuple(completed_flows[0].shape[-2:]):
+            raise ValueError("The spatial sizes of input and flow are not the same.")     # flow_loss_utils.py:25-27
+        b = masked_frames.shape[0]
+        fr, mk = [], []
+        for i in range(b):
+            f, m = ops.img_prop_scan(masked_frames[i].contiguous().float(), completed_flows[0][i].contiguous().float(),
+                                     completed_flows[1][i].contiguous().float(), masks[i].contiguous().float(),
+                                     interpolation == "nearest")
+            fr.append(f)
+            mk.append(m)
+        return torch.stack(fr, 0), torch.stack(mk, 0)
+
+    # ------------------------------------------------------------------ conv trunk
+    def _encoder(self, x):
+        """Encoder.forward propainter.py:218-232; x [n,8,H,W] channels_last (5 real + 3 zero channels)."""
+        out = _lrelu(conv(x, self._wb("encoder.layers.0", 8), 2, 1))
+        out = _lrelu(conv(out, self._wb("encoder.layers.2"), 1, 1))
+        out = _lrelu(conv(out, self._wb("encoder.layers.4"), 2, 1))
+        out = _lrelu(conv(out, self._wb("encoder.layers.6"), 1, 1))
+        x0 = as_pm(out)                                                       # [n,h,w,256]
+        n, h, w, _ = x0.shape
+        out = _lrelu(conv(out, self._wb("encoder.layers.8"), 1, 1))
+        for i, g in ((10, 2), (12, 4), (14, 8), (16, 1)):
+            o = as_pm(out)
+            mix = torch.cat([x0.view(n, h, w, g, -1), o.view(n, h, w, g, -1)], -1).view(n, h, w, -1)   # group-wise skip
+            out = _lrelu(conv(as_nchw(mix), self._wb(f"encoder.layers.{i}"), 1, 1, 1, g))
+        return out
+
+    def _up2_conv(self, key, x):
+        return conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True), self._wb(key + ".conv"), 1, 1)
+
+    def _decoder(self, x):
+        x = _lrelu(self._up2_conv("decoder.0", x))
+        x = _lrelu(conv(x, self._wb("decoder.2"), 1, 1))
+        x = _lrelu(self._up2_conv("decoder.4", x))
+        return conv(x, self._wb("decoder.6"), 1, 1)
+
+    # ------------------------------------------------------------------ learnable feature propagation
+    def _feat_propagation(self, x, dsf, dsb, pmask, interpolation):
+        """BidirectionalPropagation(128, learnable=True).forward propainter.py:104-190.
+        x [lt,h,w,128] pixel-major; dsf/dsb [lt-1,h,w,2]; pmask [lt,h,w,2] -> fused [lt,128,h,w]."""
+        if interpolation != "bilinear":
+            raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
+        lt, h, w, C = x.shape
+        dev = x.device
+        fp = "feat_prop_module."
+        cond = torch.empty(1, h, w, 2 * C + 8, device=dev)      # 261 -> 264 channels
+        bb = torch.empty(1, h, w, 2 * C + 4, device=dev)        # 258 -> 260 channels
+        src = x
+        outs = {}
+        for name in ("backward_1", "forward_1"):
+            bwd = name == "backward_1"
+            order = list(range(lt))[::-1] if bwd else list(range(lt))
+            dst = torch.empty(lt, h, w, C, device=dev)
+            dw, db = self._dcn(name)
+            prev = None
+            for i, idx in enumerate(order):
+                if i == 0:
+                    ops.prop_cond(src[idx], None, None, None, pmask[idx], None, bb[0], True)
+                else:
+                    fprop, fchk = (dsf[idx], dsb[idx]) if bwd else (dsb[idx - 1], dsf[idx - 1])
+                    ops.prop_cond(src[idx], prev, fprop, fchk, pmask[idx], cond[0], bb[0], False)
+                    p = f"{fp}deform_align.{name}.conv_offset."
+                    o = F.leaky_relu_(conv(as_nchw(cond), self._wb(p + "0", 2 * C + 8), 1, 1), 0.1)
+                    o = F.leaky_relu_(conv(o, self._wb(p + "2"), 1, 1), 0.1)
+                    o = F.leaky_relu_(conv(o, self._wb(p + "4"), 1, 1), 0.1)
+                    o = as_pm(conv(o, self._wb(p + "6"), 1, 1))
+                    ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C])
+                y = conv(_lrelu(conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1)),
+                         self._wb(f"{fp}backbone.{name}.2"), 1, 1)
+                torch.add(bb[0, :, :, C:2 * C], as_pm(y)[0], out=dst[idx])
+                prev = dst[idx]
+            outs[name] = dst
+            src = dst                                            # forward scan consumes the backward features (:138)
+        z = torch.cat([outs["backward_1"], outs["forward_1"], pmask, pmask.new_zeros(lt, h, w, 2)], -1)
+        z = conv(_lrelu(conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1)), self._wb(fp + "fuse.2"), 1, 1)
+        return z + as_nchw(x)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, masked_frames, completed_flows, masks_in, masks_updated, num_local_frames,
+                interpolation="bilinear", t_dilation=2):
+        """propainter.py:319-372 (eval).  masked_frames [b,t,3,H,W], flows 2x[b,lt-1,2,H,W],
+        masks [b,t,1,H,W] -> [b,lt,3,H,W] in (-1,1)."""
+        lt = num_local_frames
+        b, t, _, H, W = masked_frames.shape
+        if H % 8 or W % 8:
+            raise ValueError("H and W must be multiples of 8 (inference_propainter.py:34-45)")
+        res = []
+        for bi in range(b):
+            fr, mi, mu = masked_frames[bi].float(), masks_in[bi].float(), masks_updated[bi].float()
+            x = torch.cat([fr, mi, mu, fr.new_zeros(t, 3, H, W)], 1).contiguous(memory_format=torch.channels_last)
+            enc = self._encoder(x)                                                  # [t,128,h,w]
+            h, w = enc.shape[-2:]
+            dsf, dsb, pmask = ops.gen_prep(completed_flows[0][bi].contiguous().float(),
+                                           completed_flows[1][bi].contiguous().float(),
+                                           mi.contiguous(), mu.contiguous(), lt)
+            fh, fw = token_grid((h, w))
+            H2, W2 = padded_grid(fh, fw, WIN)
+            flags = ops.window_mask(pmask, fh, fw, H2 // WIN[0], W2 // WIN[1])
+            enc_pm = as_pm(enc)
+            local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
+            enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
+            tok = self.tx.soft_split(enc2)
+            tok = self.tx.run(tok, (h, w), flags, t_dilation)
+            enc3 = enc2 + self.tx.soft_comp(tok, (h, w))
+            out = torch.tanh(self._decoder(enc3[:lt]))
+            res.append(out.contiguous())
+        return torch.stack(res, 0).view(b, lt, 3, H, W)

@@ -1,0 +1,148 @@
+"""Recurrent flow completion network on the B200 hot path.
+
+Drop-in for model/recurrent_flow_completion.py:203-347 of the reference (constructor, ``forward``,
+``forward_bidirect_flow``, ``combine_flow``, state_dict incl. the training-only edge head).
+Execution plan: every (1,k,k) Conv3d is a 2-D conv over the frame batch and every (3,1,1) dilated
+temporal Conv3d one 1x1 conv over three time-shifted copies (both channels-last, cuDNN); the
+second-order deformable alignment of the bidirectional scan (:9-44, :67-124) is
+``ops.deform_align`` -- 5*tanh offset prep, sigmoid modulation, bilinear gather and the 2304-deep
+GEMM in one kernel, reading the two previous states straight out of the scan buffer.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .._params import ParamNet
+from ..nn_util import as_nchw, as_pm, cl, conv
+from ..schemas import rfc_schema
+
+
+def _lrelu(x, s=0.2):
+    return F.leaky_relu_(x, s)
+
+
+class RecurrentFlowCompleteNet(ParamNet):
+    def __init__(self, model_path=None, seed=None):
+        super().__init__(rfc_schema(), seed=seed)
+        if model_path is not None:
+            print("Pretrained flow completion model has loaded...")
+            self.load_state_dict(torch.load(model_path, map_location="cpu"), strict=True)
+
+    # ------------------------------------------------------------------ packed weights
+    def _w2d(self, key):
+        """spatial Conv3d (1,k,k) or Conv2d weight -> 2-D channels_last (weight, bias)."""
+        def build():
+            w = self.P[key + ".weight"]
+            if w.dim() == 5:
+                w = w[:, :, 0]
+            return cl(w), self.P[key + ".bias"].contiguous()
+        return self.packed("w2d:" + key, build)
+
+    def _wt(self, key):
+        """temporal Conv3d (3,1,1) weight [co,ci,3,1,1] -> 1x1 conv over [x(t-2) | x(t) | x(t+2)]."""
+        def build():
+            w = self.P[key + ".weight"][:, :, :, 0, 0]                      # [co,ci,3]
+            w = w.permute(0, 2, 1).reshape(w.shape[0], -1, 1, 1)             # [co, 3*ci] tap-major
+            return cl(w), self.P[key + ".bias"].contiguous()
+        return self.packed("wt:" + key, build)
+
+    def _offset_w0(self, name):
+        """conv_offset.0 input channels reordered from [prop|cur|n2] (:96) to our scan-buffer order
+        [prop|n2|cur] so deform input and condition share one buffer."""
+        def build():
+            w = self.P[f"feat_prop_module.deform_align.{name}.conv_offset.0.weight"]
+            w = torch.cat([w[:, :128], w[:, 256:384], w[:, 128:256]], 1)
+            return cl(w), self.P[f"feat_prop_module.deform_align.{name}.conv_offset.0.bias"].contiguous()
+        return self.packed("off0:" + name, build)
+
+    def _dcn(self, name):
+        def build():
+            p = f"feat_prop_module.deform_align.{name}"
+            return ops.pack_deform_weight(self.P[p + ".weight"]), self.P[p + ".bias"].contiguous()
+        return self.packed("dcn:" + name, build)
+
+    # ------------------------------------------------------------------ blocks
+    def _p3d(self, p, x, stride):
+        """P3DBlock :148-169 on a frame batch x [t,c,h,w] (channels_last)."""
+        y = _lrelu(conv(x, self._w2d(p + ".conv1.0"), stride, 1))
+        t = y.shape[0]
+        yp = F.pad(y, (0, 0, 0, 0, 0, 0, 2, 2))                             # zero-pad time by 2 (padding=(2,0,0))
+        z = torch.cat([yp[0:t], yp[2:t + 2], yp[4:t + 4]], 1)                # dilation 2 taps
+        return conv(z, self._wt(p + ".conv2.0"))
+
+    def _up2_conv(self, key, x):
+        return conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True), self._w2d(key + ".conv"), 1, 1)
+
+    def _propagate(self, x):
+        """BidirectionalPropagation.forward :67-124.  x [t,128,h,w] channels_last -> same."""
+        t, c, h, w = x.shape
+        dev = x.device
+        xs = as_pm(x)                                                         # [t,h,w,128]
+        fp = "feat_prop_module."
+        results = {}
+        for di, name in enumerate(("backward_", "forward_")):
+            order = list(range(t))[::-1] if di == 0 else list(range(t))
+            hist = torch.zeros(t + 2, h, w, c, device=dev)                   # slots 0,1 = zero states
+            dw, db = self._dcn(name)
+            for i, idx in enumerate(order):
+                cur = xs[idx:idx + 1]
+                prop = hist[i + 1:i + 2]                                      # state of step i-1 (zeros for i=0)
+                if i > 0:
+                    n2 = hist[i:i + 1]                                        # state of step i-2 (zeros for i=1)
+                    buf = torch.cat([prop, n2, cur], -1)                      # [1,h,w,384] = deform input | cur
+                    o = _lrelu(conv(as_nchw(buf), self._offset_w0(name), 1, 1), 0.1)
+                    o = _lrelu(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1), 0.1)
+                    o = _lrelu(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1), 0.1)
+                    o = as_pm(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.6"), 1, 1))
+                    aligned = torch.empty(1, h, w, c, device=dev)
+                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, aligned[0])
+                    prop = aligned
+                parts = [cur] + ([results["backward_"][idx:idx + 1]] if di == 1 else []) + [prop]
+                f = as_nchw(torch.cat(parts, -1))
+                y = conv(_lrelu(conv(f, self._w2d(f"{fp}backbone.{name}.0"), 1, 1), 0.1),
+                         self._w2d(f"{fp}backbone.{name}.2"), 1, 1)
+                hist[i + 2] = prop[0] + as_pm(y)[0]
+            seq = hist[2:]
+            results[name] = seq.flip(0) if di == 0 else seq
+        fused = conv(as_nchw(torch.cat([results["backward_"], results["forward_"]], -1)), self._w2d(fp + "fusion"))
+        return fused + x
+
+    # ------------------------------------------------------------------ API
+    @torch.no_grad()
+    def forward(self, masked_flows, masks):
+        """:272-309 (eval).  masked_flows [b,t,2,h,w], masks [b,t,1,h,w] -> (flow [b,t,2,h,w], None)."""
+        b, t, _, h, w = masked_flows.shape
+        outs = []
+        for bi in range(b):
+            x = torch.cat([masked_flows[bi], masks[bi]], 1)                          # [t,3,h,w]
+            x = F.pad(x, (2, 2, 2, 2), mode="replicate").contiguous(memory_format=torch.channels_last)
+            x = _lrelu(conv(x, self._w2d("downsample.0"), 2, 0))
+            e1 = _lrelu(self._p3d("encoder1.0", x, 1))
+            e1 = _lrelu(self._p3d("encoder1.2", e1, 2))
+            e2 = _lrelu(self._p3d("encoder2.0", e1, 1))
+            e2 = _lrelu(self._p3d("encoder2.2", e2, 2))
+            m = e2
+            for i, d in ((0, 3), (2, 2), (4, 1)):
+                m = _lrelu(conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d))
+            fpr = self._propagate(m)
+            d2 = _lrelu(self._up2_conv("decoder2.2", _lrelu(conv(fpr, self._w2d("decoder2.0"), 1, 1)))) + e1
+            d1 = _lrelu(self._up2_conv("decoder1.2", _lrelu(conv(d2, self._w2d("decoder1.0"), 1, 1))))
+            fl = self._up2_conv("upsample.2", _lrelu(conv(d1, self._w2d("upsample.0"), 1, 1)))
+            outs.append(fl.contiguous())
+        return torch.stack(outs, 0).view(b, t, 2, h, w), None
+
+    @torch.no_grad()
+    def forward_bidirect_flow(self, masked_flows_bi, masks):
+        """:312-337 (eval).  flows (f,b) each [b,t-1,2,h,w]; masks [b,t,1,h,w]."""
+        mf, mb = masks[:, :-1].contiguous(), masks[:, 1:].contiguous()
+        pf, _ = self.forward(masked_flows_bi[0] * (1 - mf), mf)
+        pb, _ = self.forward(torch.flip(masked_flows_bi[1] * (1 - mb), dims=[1]), torch.flip(mb, dims=[1]))
+        return [pf, torch.flip(pb, dims=[1])], [None, None]
+
+    @torch.no_grad()
+    def combine_flow(self, masked_flows_bi, pred_flows_bi, masks):
+        """:340-347."""
+        mf, mb = masks[:, :-1].contiguous(), masks[:, 1:].contiguous()
+        return (pred_flows_bi[0] * mf + masked_flows_bi[0] * (1 - mf),
+                pred_flows_bi[1] * mb + masked_flows_bi[1] * (1 - mb))

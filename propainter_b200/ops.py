@@ -1,0 +1,221 @@
+"""Tensor-level wrappers over the C ABI.  Each takes/returns torch CUDA tensors, passes raw pointers +
+the current stream, and raises on any non-zero return code.  fp32 only."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import PPAttnParams, PPWindowIds, check
+
+LOG2E = 1.4426950408889634
+
+# number of kernels of libpropainter_b200.so launched so far (bench.py reports the delta as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("propainter_b200 ops need CUDA tensors (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _dense(t):
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return t
+
+
+def _pm(t):
+    """pixel-major view [..., C] whose pixels are `ld` elements apart -> (ptr, ld)."""
+    if t.stride(-1) != 1:
+        raise RuntimeError("channel dim must be unit-stride")
+    ld = t.stride(-2)
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != exp:
+            raise RuntimeError("pixel-major view must be dense over its pixels")
+        exp *= t.shape[d]
+    return _p(t), ld
+
+
+def corr_ld(w):
+    return (w + 3) & ~3
+
+
+def corr_alloc(n_pairs, h, w, device):
+    """Pyramid buffers [n_pairs*h*w, h>>l, ld_l] (zero-filled once so the row padding is defined)."""
+    lv, hl, wl = [], h, w
+    for _ in range(4):
+        lv.append(torch.zeros(n_pairs * h * w, hl, corr_ld(wl), device=device, dtype=torch.float32))
+        hl, wl = hl // 2, wl // 2
+    return lv
+
+
+def _level_array(levels):
+    return (ctypes.c_void_p * 4)(*[lv.data_ptr() for lv in levels])
+
+
+def corr_build(fmap, idx1, idx2, levels, h, w):
+    """fmap [frames, h*w, D] pixel-major; idx1/idx2 int32 CUDA [n_pairs]; fills the 4 pyramid levels."""
+    L = _lib.lib()
+    n_pairs = idx1.numel()
+    D = fmap.shape[-1]
+    check(L.pp_corr_build(_p(_dense(fmap)), D, _p(idx1, torch.int32), _p(idx2, torch.int32), n_pairs, _p(levels[0]), h, w,
+                          _stream()), "pp_corr_build")
+    check(L.pp_corr_pool_pyramid(_level_array(levels), n_pairs * h * w, h, w, _stream()), "pp_corr_pool_pyramid")
+    _count(4)
+
+
+def corr_lookup(levels, coords, out=None):
+    """coords [B,h,w,2] -> [B,h,w,324]."""
+    B, h, w, _ = coords.shape
+    if out is None:
+        out = torch.empty(B, h, w, 324, device=coords.device, dtype=torch.float32)
+    check(_lib.lib().pp_corr_lookup(_level_array(levels), _p(_dense(coords)), _p(_dense(out)), B, h, w, _stream()),
+          "pp_corr_lookup")
+    _count(1)
+    return out
+
+
+def convex_upsample(mask_pm, flow_lr, mask_scale=0.25):
+    """mask_pm [n,h,w,576] pixel-major, flow_lr [n,h,w,2] -> planar [n,2,8h,8w]."""
+    n, h, w, _ = flow_lr.shape
+    mp, ld = _pm(mask_pm)
+    out = torch.empty(n, 2, 8 * h, 8 * w, device=flow_lr.device, dtype=torch.float32)
+    check(_lib.lib().pp_convex_upsample(mp, ld, mask_scale, _p(_dense(flow_lr)), _p(out), n, h, w, _stream()),
+          "pp_convex_upsample")
+    _count(1)
+    return out
+
+
+def img_prop_scan(frames, flows_f, flows_b, masks, nearest=True):
+    """frames [t,3,H,W], flows [t-1,2,H,W], masks [t,1,H,W] (planar) -> (frames_out, masks_out)."""
+    L = _lib.lib()
+    t, _, H, W = frames.shape
+    ws_bytes = L.pp_img_prop_scan_workspace_bytes(t, H, W)
+    ws = torch.empty(ws_bytes // 4, device=frames.device, dtype=torch.float32)
+    of, om = torch.empty_like(frames), torch.empty_like(masks)
+    check(L.pp_img_prop_scan(_p(_dense(frames)), _p(_dense(flows_f)), _p(_dense(flows_b)), _p(_dense(masks)), _p(of),
+                             _p(om), _p(ws), ws_bytes, t, H, W, int(bool(nearest)), _stream()), "pp_img_prop_scan")
+    _count(2 * (t - 1))
+    return of, om
+
+
+def prop_cond(cur, prop, fprop, fcheck, mcur, cond, bb, first):
+    """cur/prop [h,w,C] pixel-major views; fprop/fcheck/mcur [h,w,2]; cond [h,w,ldc]; bb [h,w,ldb]."""
+    h, w, C = cur.shape
+    cp, ldc = _pm(cur)
+    pp_, ldp = _pm(prop) if prop is not None else (None, ldc)
+    cdp, ldcd = _pm(cond) if cond is not None else (None, 2 * C + 8)
+    bp, ldb = _pm(bb)
+    check(_lib.lib().pp_prop_cond(cp, ldc, pp_, ldp, _p(fprop), _p(fcheck), _p(_dense(mcur)), cdp, ldcd, bp, ldb, h, w,
+                                  C, int(bool(first)), _stream()), "pp_prop_cond")
+    _count(1)
+
+
+def deform_align(x, o, flow, max_res, w_packed, bias, out):
+    """x [H,W,Cin] view, o [H,W,>=432] view, flow [H,W,2]|None, out [H,W,128] view (all pixel-major)."""
+    H, W, Cin = x.shape
+    xp, ldx = _pm(x)
+    op, ldo = _pm(o)
+    outp, ldout = _pm(out)
+    check(_lib.lib().pp_deform_align(xp, ldx, op, ldo, _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp,
+                                     ldout, H, W, Cin, out.shape[-1], _stream()), "pp_deform_align")
+    _count(1)
+    return out
+
+
+def pack_deform_weight(weight):
+    """[Cout,Cin,3,3] -> [9*Cin, Cout], row = tap*Cin + c."""
+    co, ci = weight.shape[:2]
+    return weight.permute(2, 3, 1, 0).reshape(9 * ci, co).contiguous()
+
+
+def gen_prep(flows_f, flows_b, masks_in, masks_upd, lt):
+    """planar flows [lt-1,2,H,W], masks [>=lt,1,H,W] -> dsf, dsb [lt-1,h,w,2], pmask [lt,h,w,2]."""
+    H, W = masks_in.shape[-2:]
+    h, w = H // 4, W // 4
+    dev = masks_in.device
+    dsf = torch.empty(max(lt - 1, 1), h, w, 2, device=dev, dtype=torch.float32)
+    dsb = torch.empty_like(dsf)
+    pmask = torch.empty(lt, h, w, 2, device=dev, dtype=torch.float32)
+    check(_lib.lib().pp_gen_prep(_p(_dense(flows_f)), _p(_dense(flows_b)), _p(_dense(masks_in)), _p(_dense(masks_upd)),
+                                 _p(dsf), _p(dsb), _p(pmask), lt, H, W, _stream()), "pp_gen_prep")
+    _count(1)
+    return dsf[:lt - 1], dsb[:lt - 1], pmask
+
+
+def window_mask(pmask, fh, fw, nwh, nww):
+    lt, h, w, _ = pmask.shape
+    flags = torch.empty(nwh * nww, device=pmask.device, dtype=torch.int32)
+    check(_lib.lib().pp_window_mask(_p(_dense(pmask)), lt, h, w, fh, fw, nwh, nww, _p(flags, torch.int32), _stream()),
+          "pp_window_mask")
+    _count(1)
+    return flags
+
+
+def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, out=None, WN=45, C=512):
+    """qkv [t,NT,3C]; pool_kv [t,NP,2C]; key_tok int32 [nwin,NKO]; flags int32 [nwin] -> out [t,NT,C]."""
+    if out is None:
+        out = torch.empty(t, NT, C, device=qkv.device, dtype=torch.float32)
+    prm = PPAttnParams()
+    prm.qkv, prm.pool = qkv.data_ptr(), pool_kv.data_ptr()
+    prm.key_tok, prm.flags, prm.out = key_tok.data_ptr(), flags.data_ptr(), out.data_ptr()
+    prm.ld_qkv, prm.ld_pool, prm.ld_out = qkv.stride(-2), pool_kv.stride(-2), out.stride(-2)
+    prm.t, prm.NT, prm.WN, prm.NKO, prm.NP, prm.C = t, NT, WN, key_tok.shape[1], pool_kv.shape[1], C
+    prm.kf_start, prm.kf_step = kf_start, kf_step
+    prm.nkf = len(range(kf_start, t, kf_step))
+    prm.scale_log2 = LOG2E / math.sqrt(128.0)
+    for tns, dt in ((qkv, torch.float32), (pool_kv, torch.float32), (key_tok, torch.int32), (flags, torch.int32)):
+        _p(_dense(tns), dt)
+    check(_lib.lib().pp_sparse_window_attn(ctypes.byref(prm), key_tok.shape[0], _stream()), "pp_sparse_window_attn")
+    _count(2)
+    return out
+
+
+def ffn_overlap_add(Y, frames, h, w, CH=40):
+    """Y [frames*fh*fw, 49*CH] (tap-major columns) -> gelu(unfold(fold(Y)/norm)) same shape."""
+    L = _lib.lib()
+    Z = torch.empty_like(Y)
+    ws_bytes = L.pp_ffn_overlap_add_workspace_bytes(frames, h, w, CH)
+    ws = torch.empty(ws_bytes // 4, device=Y.device, dtype=torch.float32)
+    check(L.pp_ffn_overlap_add(_p(_dense(Y)), Y.shape[-1], _p(Z), Z.shape[-1], frames, h, w, CH, _p(ws), ws_bytes,
+                               _stream()), "pp_ffn_overlap_add")
+    _count(2)
+    return Z
+
+
+def u8_to_frames(frames_u8):
+    """uint8 [T,H,W,3] -> float planar [T,3,H,W] in [-1,1]."""
+    T, H, W, _ = frames_u8.shape
+    out = torch.empty(T, 3, H, W, device=frames_u8.device, dtype=torch.float32)
+    check(_lib.lib().pp_u8_to_frames(_p(_dense(frames_u8), torch.uint8), _p(out), T, H, W, _stream()), "pp_u8_to_frames")
+    _count(1)
+    return out
+
+
+def composite_blend(pred, masks, ori_u8, comp_u8, frame_ids, first_flags):
+    """pred [n,3,H,W]; masks [T,1,H,W]; ori/comp uint8 [T,H,W,3] (comp updated in place)."""
+    n, _, H, W = pred.shape
+    ids = PPWindowIds()
+    ids.n = n
+    for i, (f, fl) in enumerate(zip(frame_ids, first_flags)):
+        ids.frame[i], ids.first[i] = int(f), int(fl)
+    check(_lib.lib().pp_composite_blend_u8(_p(_dense(pred)), _p(_dense(masks)), _p(_dense(ori_u8), torch.uint8),
+                                           _p(_dense(comp_u8), torch.uint8), ctypes.byref(ids), H, W, _stream()),
+          "pp_composite_blend_u8")
+    _count(1)

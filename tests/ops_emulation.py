@@ -1,0 +1,140 @@
+"""TEST HARNESS ONLY.  CPU stand-ins for ``propainter_b200.ops`` (built from tests/hostsim and plain torch)
+that the CPU test-suite monkeypatches in, so the *host-side plumbing* of the drop-in modules -- weight
+packing, channel orders of the concat buffers, scan bookkeeping, stage scheduling -- is checked against
+the oracle without a GPU.  The product never imports this file and has no CPU path; the GPU tests run
+the real kernels.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn.functional as F
+
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+def _fp(t):
+    assert t.dtype == torch.float32 and t.is_contiguous() and not t.is_cuda
+    return ctypes.cast(t.data_ptr(), FP)
+
+
+def install(monkeypatch, hostsim):
+    from propainter_b200 import ops
+
+    def corr_build(fmap, idx1, idx2, levels, h, w):
+        from oracle import ops_ref
+        F_, N, D = fmap.shape
+        fm = fmap.view(F_, h, w, D).permute(0, 3, 1, 2)
+        pyr = ops_ref.corr_pyramid(fm[idx1.long()], fm[idx2.long()])
+        wl = w
+        for lv, p in zip(levels, pyr):
+            lv[:, :, :wl] = p[:, 0]
+            wl //= 2
+
+    def corr_lookup(levels, coords, out=None):
+        B, h, w, _ = coords.shape
+        if out is None:
+            out = torch.empty(B, h, w, 324)
+        c = coords.contiguous()
+        hostsim.hs_corr_lookup(_fp(levels[0]), _fp(levels[1]), _fp(levels[2]), _fp(levels[3]), _fp(c), _fp(out),
+                               ctypes.c_long(B * h * w), h, w)
+        return out
+
+    def convex_upsample(mask_pm, flow_lr, mask_scale=0.25):
+        n, h, w, _ = flow_lr.shape
+        m, fl = mask_pm.contiguous(), flow_lr.contiguous()
+        out = torch.empty(n, 2, 8 * h, 8 * w)
+        hostsim.hs_convex_upsample(_fp(m), m.shape[-1], ctypes.c_float(mask_scale), _fp(fl), _fp(out), n, h, w)
+        return out
+
+    def img_prop_scan(frames, flows_f, flows_b, masks, nearest=True):
+        t, _, H, W = frames.shape
+        of, om = torch.empty_like(frames), torch.empty_like(masks)
+        a, b, c, d = frames.contiguous(), flows_f.contiguous(), flows_b.contiguous(), masks.contiguous()
+        hostsim.hs_img_prop_scan(_fp(a), _fp(b), _fp(c), _fp(d), _fp(of), _fp(om), t, H, W, int(bool(nearest)))
+        return of, om
+
+    def prop_cond(cur, prop, fprop, fcheck, mcur, cond, bb, first):
+        h, w, C = cur.shape
+        assert cur.stride(-1) == 1 and bb.stride(-1) == 1
+        args = [_fp_view(cur), cur.stride(-2), _fp_view(prop) if prop is not None else None,
+                prop.stride(-2) if prop is not None else C, _fp(fprop) if fprop is not None else None,
+                _fp(fcheck) if fcheck is not None else None, _fp(mcur.contiguous()),
+                _fp_view(cond) if cond is not None else None, cond.stride(-2) if cond is not None else 2 * C + 8,
+                _fp_view(bb), bb.stride(-2), h, w, C, int(bool(first))]
+        hostsim.hs_prop_cond(*args)
+
+    def _fp_view(t):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1
+        return ctypes.cast(t.data_ptr(), FP)
+
+    def deform_align(x, o, flow, max_res, w_packed, bias, out):
+        H, W, Cin = x.shape
+        cols = torch.empty(H * W, 9 * Cin)
+        hostsim.hs_deform_cols(_fp_view(x), x.stride(-2), _fp_view(o), o.stride(-2), _fp(flow) if flow is not None else None,
+                               ctypes.c_float(max_res), _fp(cols), H, W, Cin)
+        out.copy_((cols @ w_packed + bias).view(H, W, -1))
+        return out
+
+    def gen_prep(flows_f, flows_b, masks_in, masks_upd, lt):
+        ds = lambda z: (F.interpolate(z, scale_factor=0.25, mode="bilinear", align_corners=False) / 4.0).permute(0, 2, 3, 1).contiguous()
+        nn_ = lambda z: F.interpolate(z[:lt], scale_factor=0.25, mode="nearest")[:, 0]
+        pmask = torch.stack([nn_(masks_in), nn_(masks_upd)], -1).contiguous()
+        if lt > 1:
+            return ds(flows_f), ds(flows_b), pmask
+        e = torch.zeros(0, pmask.shape[1], pmask.shape[2], 2)
+        return e, e, pmask
+
+    def window_mask(pmask, fh, fw, nwh, nww):
+        lt = pmask.shape[0]
+        mp = F.max_pool2d(pmask[..., 0][:, None], (7, 7), (3, 3), (3, 3))
+        mp = F.pad(mp, (0, nww * 9 - fw, 0, nwh * 5 - fh))
+        return (F.max_pool2d(mp, (5, 9), (5, 9)).view(lt, -1).sum(0) > 0).int()
+
+    def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, out=None, WN=45, C=512):
+        heads, ch = C // 128, 128
+        out = torch.zeros(t, NT, C)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        kf = list(range(kf_start, t, kf_step))
+        scale = 1.0 / math.sqrt(ch)
+        for wi in range(key_tok.shape[0]):
+            own = key_tok[wi, :WN].long()
+            for hd in range(heads):
+                sl = slice(hd * ch, (hd + 1) * ch)
+                if flags[wi] != 0:
+                    allk = key_tok[wi].long()
+                    K = torch.cat([torch.cat([k[f][allk][:, sl], pool_kv[f][:, :C][:, sl]], 0) for f in kf], 0)
+                    V = torch.cat([torch.cat([v[f][allk][:, sl], pool_kv[f][:, C:][:, sl]], 0) for f in kf], 0)
+                    for f in range(t):
+                        a = torch.softmax((q[f][own][:, sl] @ K.t()) * scale, -1)
+                        out[f, own, sl] = a @ V
+                else:
+                    for f in range(t):
+                        a = torch.softmax((q[f][own][:, sl] @ k[f][own][:, sl].t()) * scale, -1)
+                        out[f, own, sl] = a @ v[f][own][:, sl]
+        return out
+
+    def ffn_overlap_add(Y, frames, h, w, CH=40):
+        Y = Y.contiguous()
+        Z = torch.empty_like(Y)
+        hostsim.hs_ffn_overlap_add(_fp(Y), Y.shape[-1], _fp(Z), Z.shape[-1], frames, h, w, CH)
+        return Z
+
+    def u8_to_frames(u8):
+        T, H, W, _ = u8.shape
+        u8 = u8.contiguous()
+        out = torch.empty(T, 3, H, W)
+        hostsim.hs_u8_to_frames(ctypes.c_void_p(u8.data_ptr()), _fp(out), T, H, W)
+        return out
+
+    def composite_blend(pred, masks, ori_u8, comp_u8, frame_ids, first_flags):
+        n, _, H, W = pred.shape
+        fr = (ctypes.c_int * n)(*[int(i) for i in frame_ids])
+        fs = (ctypes.c_int * n)(*[int(bool(i)) for i in first_flags])
+        p, m = pred.contiguous(), masks.contiguous()
+        hostsim.hs_composite(_fp(p), _fp(m), ctypes.c_void_p(ori_u8.data_ptr()), ctypes.c_void_p(comp_u8.data_ptr()), n, fr,
+                             fs, H, W)
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and hasattr(ops, name) and not name.startswith("_"):
+            monkeypatch.setattr(ops, name, fn)

@@ -1,0 +1,80 @@
+"""CPU tests of the drop-in modules' host-side plumbing (weight packing, concat-buffer channel orders, scan
+bookkeeping, stage scheduling, compositing order) against the oracle, with ``propainter_b200.ops`` replaced
+by the test-only CPU stand-ins of tests/ops_emulation.py.  The kernels themselves are checked on the GPU
+(test_gpu_*.py); their per-element rules on the CPU in test_elem_hostsim.py."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import flowcomp_ref, generator_ref, ops_ref, pipeline_ref, raft_ref
+from tests import ops_emulation
+
+
+@pytest.fixture()
+def emu(monkeypatch, hostsim):
+    ops_emulation.install(monkeypatch, hostsim)
+
+
+def rel_err(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def test_raft_plumbing(emu):
+    from propainter_b200 import synth
+    from propainter_b200.model.modules.flow_comp_raft import RAFT_bi
+    net = RAFT_bi(None, "cpu", seed=1)
+    u8, _, _ = synth.make_clip(3, 128, 144, seed=3)
+    frames = pipeline_ref.to_float_frames(u8)
+    fw, bw = net(frames, iters=3)
+    rf, rb = raft_ref.raft_bi(net.fix_raft.state_dict(), frames, 3)
+    assert rel_err(fw, rf) < 1e-4 and rel_err(bw, rb) < 1e-4, (rel_err(fw, rf), rel_err(bw, rb))
+    lo, up = net.fix_raft(frames[0, :2], frames[0, 1:3], iters=2, test_mode=True)
+    rlo, rup = raft_ref.raft_forward(net.fix_raft.state_dict(), frames[0, :2], frames[0, 1:3], 2, return_lowres=True)
+    assert rel_err(up, rup) < 1e-4 and rel_err(lo, rlo) < 1e-4
+
+
+def test_flow_completion_plumbing(emu):
+    from propainter_b200.model.recurrent_flow_completion import RecurrentFlowCompleteNet
+    net = RecurrentFlowCompleteNet(None, seed=2)
+    gen = torch.Generator().manual_seed(0)
+    T, H, W = 6, 32, 48
+    flows = (torch.randn(2, T - 1, 2, H, W, generator=gen) * 3, torch.randn(2, T - 1, 2, H, W, generator=gen) * 3)
+    masks = torch.zeros(2, T, 1, H, W)
+    masks[..., 8:24, 12:36] = 1
+    pred, _ = net.forward_bidirect_flow(flows, masks)
+    ref = flowcomp_ref.forward_bidirect_flow(net.state_dict(), flows, masks)
+    assert rel_err(pred[0], ref[0]) < 1e-4 and rel_err(pred[1], ref[1]) < 1e-4, (rel_err(pred[0], ref[0]), rel_err(pred[1], ref[1]))
+
+
+@pytest.mark.parametrize("H,W,t,lt", [(64, 96, 4, 3), (128, 128, 3, 2), (64, 64, 2, 1)])
+def test_generator_plumbing(emu, H, W, t, lt):
+    from propainter_b200.model.propainter import InpaintGenerator
+    net = InpaintGenerator(seed=3)
+    gen = torch.Generator().manual_seed(1)
+    frames = torch.rand(1, t, 3, H, W, generator=gen) * 2 - 1
+    sm = lambda z: F.avg_pool2d(z.view(-1, 2, H, W), 9, 1, 4).view(z.shape)
+    flows = (sm(torch.randn(1, lt - 1, 2, H, W, generator=gen) * 12), sm(torch.randn(1, lt - 1, 2, H, W, generator=gen) * 12))
+    masks = torch.zeros(1, t, 1, H, W)
+    masks[..., H // 4:H // 2, W // 3:2 * W // 3] = 1
+    upd = masks * (torch.rand(1, t, 1, H, W, generator=gen) > 0.5).float()
+    mf = frames * (1 - masks)
+    out = net(mf, flows, masks, upd, lt)
+    ref = generator_ref.generator_forward(net.state_dict(), mf, flows, masks, upd, lt)
+    assert out.shape == ref.shape and rel_err(out, ref) < 2e-4, rel_err(out, ref)
+
+
+def test_pipeline_plumbing(emu):
+    from propainter_b200 import synth
+    from propainter_b200.inference_propainter import InferenceConfig, ProPainterPipeline
+    T, H, W = 13, 128, 128
+    u8, fm, md = synth.make_clip(T, H, W, mask="ellipse", seed=0)
+    pipe = ProPainterPipeline(device="cpu")
+    cfg = InferenceConfig(raft_iter=1, subvideo_length=6)              # forces halo chunking in stages 2/3
+    comp, st = pipe(torch.from_numpy(u8), fm, md, cfg, return_stages=True)
+    ref, rst = pipeline_ref.run_pipeline(pipe.state_dicts(), u8, fm, md, raft_iter=1, subvideo_length=6, return_stages=True)
+    for k in (0, 1):
+        assert rel_err(st["gt_flows"][k], rst["gt_flows"][k]) < 1e-4
+        assert rel_err(st["pred_flows"][k], rst["pred_flows"][k]) < 1e-3
+    assert (st["updated_masks"] != rst["updated_masks"]).float().mean() < 2e-3
+    assert ops_ref.psnr_u8(comp.numpy(), ref) > 50.0
