@@ -105,6 +105,44 @@ def run_reference(args, wl):
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_reference_cuda(args, wl):
+    """Informational arm (not part of the driver contract): the same oracle on cuda:0, i.e. the reference's
+    stock PyTorch-CUDA execution plan (library kernels, per-window .cpu() compositing), with the real
+    torchvision.ops.deform_conv2d in place of the oracle's gather restatement.  This is the denominator of
+    north_star's ">= 10x the reference PyTorch-CUDA path" target."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torchvision
+    from oracle import flowcomp_ref, generator_ref, pipeline_ref
+    from propainter_b200 import schemas, synth
+    from propainter_b200._params import ParamNet
+
+    def tv_deform(x, offset, mask, weight, bias):
+        return torchvision.ops.deform_conv2d(x, offset, weight, bias, 1, 1, 1, mask)
+    flowcomp_ref.deform_conv3x3 = tv_deform
+    generator_ref.deform_conv3x3 = tv_deform
+    dev = torch.device("cuda:0")
+    u8, fm, md = synth.make_clip(wl["T"], wl["H"], wl["W"], mask=wl["mask"], seed=0)
+    fm, md = fm.to(dev), md.to(dev)
+    sds = {k: {n: v.to(dev) for n, v in ParamNet(sch, seed=sd).state_dict().items()}
+           for k, sch, sd in (("raft", schemas.raft_schema(), 1), ("rfc", schemas.rfc_schema(), 2), ("gen", schemas.generator_schema(), 3))}
+    times = []
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipeline_ref.run_pipeline(sds, u8, fm, md, raft_iter=wl["raft_iter"])
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    print(json.dumps({"impl": "reference-cuda", "metric": METRIC, "value": wl["T"] * len(times) / tot, "unit": "frames/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+                      "higher_is_better": True, "dtype": "f32 (torch defaults: cuDNN TF32 on, matmul TF32 off)",
+                      "data": "synthetic", "config": {"workload": wl["name"], "note": "stock torch/torchvision kernels, "
+                                                      "no empty_cache() calls (the reference's would only slow it)"}}))
+
+
 def cpu_baseline(wl, budget_s=40.0):
     import torch
     from oracle import pipeline_ref
@@ -252,13 +290,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args, wl)
     else:
         run_ours(args, wl)
 

@@ -36,6 +36,9 @@ int pp_corr_pool_pyramid(float* const* levels, long planes, int h, int w, cudaSt
  * coords [n_pairs*h*w][2] (x,y) -> out pixel-major [n_pairs*h*w][324]. */
 int pp_corr_lookup(const float* const* levels, const float* coords, float* out, long n_pairs, int h, int w,
                    cudaStream_t stream);
+/* same contract, plain global loads instead of TMA staging (baseline for the ncu comparison) */
+int pp_corr_lookup_ldg(const float* const* levels, const float* coords, float* out, long n_pairs, int h, int w,
+                       cudaStream_t stream);
 /* RAFT.upsample_flow RAFT/raft.py:73-84.  mask pixel-major [n*h*w][ld_mask>=576] (unscaled conv output,
  * mask_scale = 0.25 from update.py:135); flow_lr [n][h][w][2]; out planar [n][2][8h][8w]. */
 int pp_convex_upsample(const float* mask, int ld_mask, float mask_scale, const float* flow_lr, float* out, int n,
@@ -93,6 +96,15 @@ int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t s
 size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH);
 int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH, void* workspace,
                        size_t ws_bytes, cudaStream_t stream);
+
+/* ---- conv epilogues ------------------------------------------------------------------------- */
+/* In-place y = act(x + bias[c]) on a dense pixel-major tensor [n_pix][C]: replaces the bias add of
+ * F.conv2d plus the ReLU / LeakyReLU / sigmoid / tanh that follows it at every conv of the three nets.
+ * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh. */
+int pp_bias_act(float* x, const float* bias, long n_pix, int C, int act, float slope, cudaStream_t stream);
+/* `deconv` up-sampling, F.interpolate(scale_factor=2, bilinear, align_corners=True)
+ * (model/propainter.py:248-253, model/recurrent_flow_completion.py:141-146); pixel-major [n][h][w][C] -> [n][2h][2w][C]. */
+int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h, int w, int C, cudaStream_t stream);
 
 /* ---- driver-side pixel ops (inference_propainter.py) ----------------------------------------- */
 /* to_tensors()(frames)*2-1  core/utils.py:130-170 + inference_propainter.py:264: uint8 [T][H][W][3] -> planar float */

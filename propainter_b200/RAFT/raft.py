@@ -57,10 +57,10 @@ class RAFT(ParamNet):
         inst = p == "fnet"
 
         def cn(key, bn, t, stride=1, pad=1, relu=True):
-            y = conv(t, self._wb(key, None if inst else bn), stride, pad)
-            if inst:
-                y = F.instance_norm(y, eps=1e-5)
-            return F.relu_(y) if relu else y
+            if inst:                                            # conv -> InstanceNorm -> ReLU
+                y = F.instance_norm(conv(t, self._wb(key), stride, pad), eps=1e-5)
+                return F.relu_(y) if relu else y
+            return conv(t, self._wb(key, bn), stride, pad, act="relu" if relu else "none")    # BN folded
 
         x = cn(p + ".conv1", p + ".norm1", x, 2, 3)
         for li, stride in ((1, 1), (2, 2), (3, 2)):
@@ -102,22 +102,22 @@ class RAFT(ParamNet):
         for _ in range(iters):
             ops.corr_lookup(levels, c1, corr)
             flow = as_nchw(c1 - c0)
-            cor = F.relu_(conv(as_nchw(corr), self._wb(u + "encoder.convc1")))
-            cor = F.relu_(conv(cor, self._wb(u + "encoder.convc2"), 1, 1))
-            flo = F.relu_(conv(flow, self._wb(u + "encoder.convf1"), 1, 3))
-            flo = F.relu_(conv(flo, self._wb(u + "encoder.convf2"), 1, 1))
-            mot = F.relu_(conv(torch.cat([cor, flo], 1), self._wb(u + "encoder.conv"), 1, 1))
+            cor = conv(as_nchw(corr), self._wb(u + "encoder.convc1"), act="relu")
+            cor = conv(cor, self._wb(u + "encoder.convc2"), 1, 1, act="relu")
+            flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
+            flo = conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu")
+            mot = conv(torch.cat([cor, flo], 1), self._wb(u + "encoder.conv"), 1, 1, act="relu")
             x = torch.cat([inp, mot, flow], 1)
             for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
                 hx = torch.cat([net, x], 1)
-                zr = torch.sigmoid_(conv(hx, self._gates(tag), 1, pad))
+                zr = conv(hx, self._gates(tag), 1, pad, act="sigmoid")
                 z, r = zr[:, :128], zr[:, 128:]
-                q = torch.tanh_(conv(torch.cat([r * net, x], 1), self._wb(u + f"gru.convq{tag}"), 1, pad))
+                q = conv(torch.cat([r * net, x], 1), self._wb(u + f"gru.convq{tag}"), 1, pad, act="tanh")
                 net = torch.lerp(net, q, z)                     # (1-z)*h + z*q
-            d = conv(F.relu_(conv(net, self._wb(u + "flow_head.conv1"), 1, 1)), self._wb(u + "flow_head.conv2"), 1, 1)
+            d = conv(conv(net, self._wb(u + "flow_head.conv1"), 1, 1, act="relu"), self._wb(u + "flow_head.conv2"), 1, 1)
             c1 = c1 + as_pm(d)
         flow_lr = c1 - c0
-        mask = conv(F.relu_(conv(net, self._wb(u + "mask.0"), 1, 1)), self._wb(u + "mask.2"))
+        mask = conv(conv(net, self._wb(u + "mask.0"), 1, 1, act="relu"), self._wb(u + "mask.2"))
         up = ops.convex_upsample(as_pm(mask), flow_lr.contiguous(), 0.25)
         return as_nchw(flow_lr), up
 
@@ -133,7 +133,11 @@ class RAFT(ParamNet):
 
     @torch.no_grad()
     def flows_bidirectional(self, frames, iters=20):
-        """frames [l,3,H,W] -> (forward flows i->i+1, backward flows i+1->i), each [l-1,2,H,W]."""
+        """frames [l,3,H,W] -> (forward flows i->i+1, backward flows i+1->i), each [l-1,2,H,W].
+        Encoders + 20 refinement iterations replay as one CUDA graph per clip shape."""
+        return self.graphs(("raft_bi", iters), lambda fr: self._flows_bidirectional(fr, iters), frames.contiguous())
+
+    def _flows_bidirectional(self, frames, iters):
         l = frames.shape[0]
         fmap, net, inp, hw = self.encode_frames(frames)
         a = torch.arange(l - 1, device=frames.device, dtype=torch.int32)

@@ -110,12 +110,16 @@ class ParamNet(nn.Module):
             _descend(self, ap[:-1]).add_module(ap[-1], tgt)
         self._flat = None
         self._packed = {}
+        from .graphs import GraphCache
+        self.graphs = GraphCache()          # captured stage graphs; dropped whenever the weights change
         self.register_load_state_dict_post_hook(lambda m, _k: m._invalidate())
         self.eval()
 
     def _invalidate(self):
         self._flat = None
         self._packed = {}
+        if hasattr(self, "graphs"):
+            self.graphs.clear()
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)

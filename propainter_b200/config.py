@@ -1,0 +1,39 @@
+"""Execution switches (module-level; read at call time).
+
+LINEAR_TF32     plain Linear layers of the transformer (q/k/v, proj, fc1, fc2 = 807 GFLOP per generator call)
+                run as TF32 tensor-core GEMMs (fp32 accumulate) instead of cuBLAS' fp32 SIMT sgemm.  Same
+                precision class as the reference's own CUDA convs (cuDNN TF32 is torch's default) and as our
+                attention / deform-align kernels.  Set False for fp32-exact library GEMMs (tests do, to
+                isolate kernel error).
+CUDNN_BENCHMARK let cuDNN autotune conv algorithms during graph warm-up.
+CUDA_GRAPHS     replay each stage as a captured CUDA graph per shape signature (propainter_b200/graphs.py).
+FUSED_EPILOGUE  conv bias + activation through pp_bias_act (one pass) instead of cuDNN's bias add_ + ATen activation.
+"""
+import contextlib
+
+import torch
+
+LINEAR_TF32 = True
+CUDNN_BENCHMARK = True
+CUDA_GRAPHS = True
+FUSED_EPILOGUE = True
+
+
+@contextlib.contextmanager
+def linear_precision():
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(LINEAR_TF32) or prev
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@contextlib.contextmanager
+def cudnn_autotune():
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = bool(CUDNN_BENCHMARK) or prev
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.benchmark = prev

@@ -1,0 +1,122 @@
+// RAFT correlation lookup, TMA-staged (sm_100a).
+//
+// One warp per source pixel.  For each of the 4 pyramid levels the warp's elected lane issues one
+// cp.async.bulk.tensor (TMA, 3-D tiled: x, y, plane) that lands the 12x12 neighbourhood of the lookup
+// centre in shared memory; out-of-range rows / columns are zero-filled by the TMA unit, which *is*
+// grid_sample's zeros padding, so the inner loop has no bounds logic on loads.  The 81 taps of a level
+// are then bilinear blends of shared-memory values and are written as one contiguous 324-float run.
+// Replaces CorrBlock.__call__ (RAFT/corr.py:29-50) + bilinear_sampler (RAFT/utils/utils.py:57-71).
+#include <cuda.h>
+#include "pp_elem.cuh"
+#include "../../include/propainter_b200.h"
+
+#define LK_WARPS 8
+#define LK_BOX 12
+#define LK_HALF 5
+#define LK_LVL_FLOATS 160               // 12*12 = 144 floats, padded to 640 B so every box is 128-byte aligned
+
+__device__ __forceinline__ uint32_t lk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ int lk_base(float c, float inv) {
+  float v = floorf(c * inv);
+  v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);
+  return (int)v - LK_HALF;
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_constant__ CUtensorMap tm0,
+    const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+    const __grid_constant__ CUtensorMap tm3, const float* __restrict__ coords, float* __restrict__ out, long npix,
+    int h, int w) {
+  __shared__ __align__(128) float patch[LK_WARPS][4][LK_LVL_FLOATS];
+  __shared__ __align__(8) unsigned long long bar[LK_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long pix = (long)blockIdx.x * LK_WARPS + warp;
+  if (pix >= npix) return;
+  const float cx = coords[2 * pix], cy = coords[2 * pix + 1];
+  const uint32_t bar_a = lk_smem(&bar[warp]);
+  int bx[4], by[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) { bx[l] = lk_base(cx, 1.0f / (float)(1 << l)); by[l] = lk_base(cy, 1.0f / (float)(1 << l)); }
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_BOX * LK_BOX * 4) : "memory");
+    const CUtensorMap* tms[4] = {&tm0, &tm1, &tm2, &tm3};
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(lk_smem(&patch[warp][l][0])), "l"(tms[l]), "r"(bx[l]), "r"(by[l]), "r"((int)pix), "r"(bar_a) : "memory");
+  }
+  __syncwarp();
+  {                                       // wait for the 4 boxes (phase 0), bounded spin
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar_a) : "memory");
+    if (!done) __trap();
+  }
+  float* o = out + pix * 324;
+  int hl = h, wl = w;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float* P = &patch[warp][l][0];
+    const float s = (float)(1 << l);
+    const float xl = PP_DIV(cx, s), yl = PP_DIV(cy, s);
+    for (int tap = lane; tap < 81; tap += 32) {
+      const int a = tap / 9, b = tap - a * 9;
+      const PPTaps t = pp_taps(pp_raft_coord(PP_ADD(xl, (float)(a - 4)), wl), pp_raft_coord(PP_ADD(yl, (float)(b - 4)), hl), hl, wl);
+      float v = 0.f;
+      if (t.any) {
+        const int px = t.x0 - bx[l], py = t.y0 - by[l];          // position inside the staged box
+        if (px >= 0 && px + 1 < LK_BOX && py >= 0 && py + 1 < LK_BOX) {
+          const float* q = P + py * LK_BOX + px;
+          v = q[0] * t.w00 + q[1] * t.w01 + q[LK_BOX] * t.w10 + q[LK_BOX + 1] * t.w11;
+        }
+      }
+      o[l * 81 + tap] = v;
+    }
+    hl >>= 1; wl >>= 1;
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled lk_encoder() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return (PFN_encodeTiled)fn;
+}
+
+extern "C" int pp_corr_lookup(const float* const* levels, const float* coords, float* out, long n_pairs, int h, int w,
+                              cudaStream_t stream) {
+  if ((h >> 3) < 2 || (w >> 3) < 2) return PP_ERR_SHAPE;
+  const long npix = n_pairs * h * w;
+  if (npix > 0x7fffffffL) return PP_ERR_SHAPE;
+  PFN_encodeTiled enc = lk_encoder();
+  if (!enc) return PP_ERR_LAUNCH;
+  CUtensorMap tm[4];
+  int hl = h, wl = w;
+  for (int l = 0; l < 4; ++l) {
+    const int ld = pp_corr_ld(wl);
+    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)hl, (cuuint64_t)npix};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)hl * ld * 4};
+    cuuint32_t box[3] = {LK_BOX, LK_BOX, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (((uintptr_t)levels[l] & 15) != 0) return PP_ERR_ALIGN;
+    CUresult r = enc(&tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)levels[l], dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return PP_ERR_LAUNCH;
+    hl >>= 1; wl >>= 1;
+  }
+  k_corr_lookup_tma<<<(int)((npix + LK_WARPS - 1) / LK_WARPS), LK_WARPS * 32, 0, stream>>>(tm[0], tm[1], tm[2], tm[3],
+                                                                                           coords, out, npix, h, w);
+  if (cudaPeekAtLastError() != cudaSuccess) return PP_ERR_LAUNCH;
+  return PP_OK;
+}

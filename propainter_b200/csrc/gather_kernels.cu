@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(256) k_corr_lookup(PPLevels lv, const float* _
   }
 }
 
-// replaces CorrBlock.__call__ (RAFT/corr.py:29-50): coords [B*h*w][2] -> out [B*h*w][324]
-extern "C" int pp_corr_lookup(const float* const* levels, const float* coords, float* out, long n_pairs, int h,
+// Plain-load variant of the lookup (kept as the measured baseline of the TMA-staged kernel in
+// corr_lookup_tma.cu; same contract as pp_corr_lookup)
+extern "C" int pp_corr_lookup_ldg(const float* const* levels, const float* coords, float* out, long n_pairs, int h,
                               int w, cudaStream_t stream) {
   if ((h >> 3) < 2 || (w >> 3) < 2) return PP_ERR_SHAPE;
   PPLevels lv;
@@ -253,26 +254,42 @@ extern "C" int pp_window_mask(const float* pmask, int lt, int h, int w, int fh, 
 }
 
 // ================================================================ fusion feed-forward overlap-add
-__global__ void __launch_bounds__(256) k_ffn_fold(const float* __restrict__ Y, int ldy, int CH, int fh, int fw, int h,
-                                                  int w, int frames, float* __restrict__ F) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over frames*h*w*CH, channel fastest
-  long total = (long)frames * h * w * CH;
-  if (i >= total) return;
-  int c = (int)(i % CH); long px = i / CH;
-  int f = (int)(px / ((long)h * w)); int r = (int)(px - (long)f * h * w); int y = r / w, x = r - y * w;
-  F[i] = pp_ffn_fold(Y + (long)f * fh * fw * ldy, ldy, CH, fh, fw, y, x, c);
+// fold (+ /count + GELU, applied once per feature pixel instead of once per (token, tap)) ...
+__global__ void __launch_bounds__(256) k_ffn_fold_gelu(const float* __restrict__ Y, int ldy, int CH, int fh, int fw, int h,
+                                                       int w, float* __restrict__ F) {
+  const int c4n = CH >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over h*w*(CH/4) of frame blockIdx.y
+  if (i >= h * w * c4n) return;
+  const int c = (i % c4n) * 4, px = i / c4n, y = px / w, x = px - y * w;
+  const float* Yf = Y + (long)blockIdx.y * fh * fw * ldy;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n = 0;
+  for (int ty = (y + 3) / 3, ky; ty >= 0 && (ky = y + 3 - 3 * ty) < 7; --ty) {
+    if (ty >= fh) continue;
+    for (int tx = (x + 3) / 3, kx; tx >= 0 && (kx = x + 3 - 3 * tx) < 7; --tx) {
+      if (tx >= fw) continue;
+      const float4 v = *reinterpret_cast<const float4*>(Yf + (long)(ty * fw + tx) * ldy + (ky * 7 + kx) * CH + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ++n;
+    }
+  }
+  const float d = (float)n;
+  float4 o;
+  o.x = pp_gelu(s.x / d); o.y = pp_gelu(s.y / d); o.z = pp_gelu(s.z / d); o.w = pp_gelu(s.w / d);
+  *reinterpret_cast<float4*>(F + ((long)blockIdx.y * h * w + px) * CH + c) = o;
 }
-__global__ void __launch_bounds__(256) k_ffn_unfold_gelu(const float* __restrict__ F, int CH, int fh, int fw, int h,
-                                                         int w, int frames, float* __restrict__ Z, int ldz) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over tokens*49*CH, channel fastest
-  long total = (long)frames * fh * fw * 49 * CH;
-  if (i >= total) return;
-  int c = (int)(i % CH); long r = i / CH; int tap = (int)(r % 49); long tok = r / 49;
-  int f = (int)(tok / ((long)fh * fw)); int tr = (int)(tok - (long)f * fh * fw); int ty = tr / fw, tx = tr - ty * fw;
-  int y = 3 * ty - 3 + tap / 7, x = 3 * tx - 3 + tap % 7;
-  float v = 0.f;
-  if (y >= 0 && y < h && x >= 0 && x < w) v = pp_gelu(F[(((long)f * h + y) * w + x) * CH + c]);
-  Z[tok * ldz + tap * CH + c] = v;
+// ... then unfold is a pure gather-copy (out-of-image taps read as gelu(0) = 0)
+__global__ void __launch_bounds__(256) k_ffn_unfold(const float* __restrict__ F, int CH, int fh, int fw, int h, int w,
+                                                    float* __restrict__ Z, int ldz) {
+  const int c4n = CH >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over fh*fw*49*(CH/4) of frame blockIdx.y
+  if (i >= fh * fw * 49 * c4n) return;
+  const int c = (i % c4n) * 4, r = i / c4n, tap = r % 49, tok = r / 49, ty = tok / fw, tx = tok - ty * fw;
+  const int y = 3 * ty - 3 + tap / 7, x = 3 * tx - 3 + tap % 7;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y >= 0 && y < h && x >= 0 && x < w)
+    v = *reinterpret_cast<const float4*>(F + (((long)blockIdx.y * h + y) * w + x) * CH + c);
+  *reinterpret_cast<float4*>(Z + ((long)blockIdx.y * fh * fw + tok) * ldz + tap * CH + c) = v;
 }
 
 extern "C" size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH) {
@@ -283,12 +300,73 @@ extern "C" size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, i
 extern "C" int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH,
                                   void* workspace, size_t ws_bytes, cudaStream_t stream) {
   const int fh = (h - 1) / 3 + 1, fw = (w - 1) / 3 + 1;
-  if (ldy < 49 * CH || ldz < 49 * CH) return PP_ERR_SHAPE;
+  if (ldy < 49 * CH || ldz < 49 * CH || frames < 1 || frames > 65535) return PP_ERR_SHAPE;
+  if (CH % 4 || ldy % 4 || ldz % 4) return PP_ERR_ALIGN;
   if (ws_bytes < pp_ffn_overlap_add_workspace_bytes(frames, h, w, CH)) return PP_ERR_WORKSPACE;
   float* F = (float*)workspace;
-  long n1 = (long)frames * h * w * CH, n2 = (long)frames * fh * fw * 49 * CH;
-  k_ffn_fold<<<pp_blocks(n1, 256), 256, 0, stream>>>(Y, ldy, CH, fh, fw, h, w, frames, F);
-  k_ffn_unfold_gelu<<<pp_blocks(n2, 256), 256, 0, stream>>>(F, CH, fh, fw, h, w, frames, Z, ldz);
+  const long n1 = (long)h * w * (CH / 4), n2 = (long)fh * fw * 49 * (CH / 4);
+  if (n2 > 0x7fffffffL) return PP_ERR_SHAPE;
+  k_ffn_fold_gelu<<<dim3(pp_blocks(n1, 256), frames), 256, 0, stream>>>(Y, ldy, CH, fh, fw, h, w, F);
+  k_ffn_unfold<<<dim3(pp_blocks(n2, 256), frames), 256, 0, stream>>>(F, CH, fh, fw, h, w, Z, ldz);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ conv epilogue + x2 upsampling
+// y = act(x + bias[c]) in place on a pixel-major tensor: one pass instead of cuDNN's separate bias
+// add_ kernel followed by the activation kernel.  act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh.
+__global__ void __launch_bounds__(256) k_bias_act(float* __restrict__ x, const float* __restrict__ bias, long n4, int C,
+                                                  int act, float slope) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % C);
+  float4 v = reinterpret_cast<float4*>(x)[i];
+  const float4 b = *reinterpret_cast<const float4*>(bias + c);
+  float r[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float t = r[k];
+    if (act == 1) t = fmaxf(t, 0.f);
+    else if (act == 2) t = t > 0.f ? t : t * slope;
+    else if (act == 3) t = 1.0f / (1.0f + expf(-t));
+    else if (act == 4) t = tanhf(t);
+    r[k] = t;
+  }
+  reinterpret_cast<float4*>(x)[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+// replaces the bias add of F.conv2d plus the following ReLU / LeakyReLU / sigmoid / tanh call
+extern "C" int pp_bias_act(float* x, const float* bias, long n_pix, int C, int act, float slope, cudaStream_t stream) {
+  if (C % 4 || ((uintptr_t)x & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
+  const long n4 = n_pix * C / 4;
+  k_bias_act<<<pp_blocks(n4, 256), 256, 0, stream>>>(x, bias, n4, C, act, slope);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+__global__ void __launch_bounds__(256) k_upsample2x(const float* __restrict__ src, float* __restrict__ dst, int n, int h,
+                                                    int w, int C) {
+  const int c4n = C >> 2, H = 2 * h, W = 2 * w;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over n*H*W*(C/4)
+  if (i >= (long)n * H * W * c4n) return;
+  const int c = (int)(i % c4n) * 4; const long px = i / c4n;
+  const int b = (int)(px / ((long)H * W)); const int r = (int)(px - (long)b * H * W); const int y = r / W, x = r - y * W;
+  const PPUp uy = pp_up2_coord(y, h), ux = pp_up2_coord(x, w);
+  const float* p = src + (((long)b * h + uy.i0) * w + ux.i0) * C + c;
+  const float4 v00 = *reinterpret_cast<const float4*>(p), v01 = *reinterpret_cast<const float4*>(p + (long)ux.step * C);
+  const float4 v10 = *reinterpret_cast<const float4*>(p + (long)uy.step * w * C);
+  const float4 v11 = *reinterpret_cast<const float4*>(p + ((long)uy.step * w + ux.step) * C);
+  float4 o;
+  o.x = pp_up2_blend(v00.x, v01.x, v10.x, v11.x, uy, ux); o.y = pp_up2_blend(v00.y, v01.y, v10.y, v11.y, uy, ux);
+  o.z = pp_up2_blend(v00.z, v01.z, v10.z, v11.z, uy, ux); o.w = pp_up2_blend(v00.w, v01.w, v10.w, v11.w, uy, ux);
+  reinterpret_cast<float4*>(dst)[i] = o;
+}
+// replaces F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) of `deconv`
+// (model/propainter.py:248-253, model/recurrent_flow_completion.py:141-146); pixel-major in/out
+extern "C" int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h, int w, int C, cudaStream_t stream) {
+  if (C % 4) return PP_ERR_ALIGN;
+  if (h < 2 || w < 2) return PP_ERR_SHAPE;
+  const long total = (long)n * 4 * h * w * (C / 4);
+  k_upsample2x<<<pp_blocks(total, 256), 256, 0, stream>>>(src, dst, n, h, w, C);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -249,6 +249,23 @@ PP_HD float pp_ffn_fold(const float* Y, int ldy, int CH, int fh, int fw, int y, 
 PP_HD float pp_gelu(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------------------------
+// x2 bilinear up-sampling with align_corners=True (ATen upsample_bilinear2d): src = dst*(in-1)/(2in-1)
+struct PPUp { int i0, step; float l0, l1; };
+PP_HD PPUp pp_up2_coord(int dst, int in) {
+  PPUp u;
+  const float scale = (float)(in - 1) / (float)(2 * in - 1);
+  const float s = scale * (float)dst;
+  u.i0 = (int)s;
+  u.step = u.i0 < in - 1 ? 1 : 0;
+  u.l1 = s - (float)u.i0;
+  u.l0 = 1.0f - u.l1;
+  return u;
+}
+PP_HD float pp_up2_blend(float v00, float v01, float v10, float v11, const PPUp& uy, const PPUp& ux) {
+  return uy.l0 * (ux.l0 * v00 + ux.l1 * v01) + uy.l1 * (ux.l0 * v10 + ux.l1 * v11);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Final compositing (inference_propainter.py:437-450): uint8 truncation, masked composite,
 // order-dependent 1/2-1/2 running blend (truncating again).
 PP_HD uint8_t pp_composite(float pred, float mask, uint8_t ori, uint8_t prev, int first) {

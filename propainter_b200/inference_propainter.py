@@ -141,13 +141,15 @@ class ProPainterPipeline:
         comp = torch.zeros_like(ori_u8) if comp is None else comp
         visited = [False] * T if visited is None else visited
         md = masks_dilated[0].contiguous()
+        # encoder features depend only on (frame, mask, updated mask): computed once per clip, not once per window
+        enc_all = self.model.encode(upd_frames[0], md, upd_masks[0])
         for wi, (nb, refs) in enumerate(plan):
             if windows is not None and wi not in windows:
                 continue
             ids = nb + refs
-            pred = self.model(upd_frames[:, ids], (pred_flows[0][:, nb[:-1]], pred_flows[1][:, nb[:-1]]),
-                              masks_dilated[:, ids], upd_masks[:, ids], len(nb))
-            ops.composite_blend(pred[0].contiguous(), md, ori_u8, comp, nb, [not visited[i] for i in nb])
+            pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                                               md[ids], upd_masks[0, ids], len(nb))
+            ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
             for i in nb:
                 visited[i] = True
         return comp

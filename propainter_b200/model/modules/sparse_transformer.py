@@ -15,7 +15,7 @@ the owning ``InpaintGenerator`` (a ParamNet); these helpers only execute.
 import torch
 import torch.nn.functional as F
 
-from ... import ops
+from ... import config, ops
 from ...nn_util import as_nchw, as_pm, cl, conv
 from ...window_index import padded_grid, token_grid, window_key_table
 
@@ -81,12 +81,16 @@ class TransformerExec:
         y = F.conv_transpose2d(as_nchw(tokens), self._sc(), None, stride=ST, padding=PD, output_padding=op)
         y = y + self._sc_bias_map(tuple(hw))
         P = self.net.P
-        return F.conv2d(y, self.net.packed("scbc", lambda: cl(P["sc.bias_conv.weight"])), P["sc.bias_conv.bias"], padding=1)
+        return conv(y, self.net.packed("scbc", lambda: (cl(P["sc.bias_conv.weight"]), P["sc.bias_conv.bias"].contiguous())), 1, 1)
 
     # ------------------------------------------------------------------ transformer
     def run(self, tokens, hw, flags, t_dilation=2):
         """tokens [t,fh,fw,C]; flags int32 [n_windows] (1 = masked window).  :294-344."""
         assert self.depths % t_dilation == 0, "wrong t_dilation input."
+        with config.linear_precision():
+            return self._run(tokens, hw, flags, t_dilation)
+
+    def _run(self, tokens, hw, flags, t_dilation):
         t, fh, fw, C = tokens.shape
         H2, W2 = padded_grid(fh, fw, WIN)
         NT = H2 * W2

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from .._params import ParamNet
-from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels
+from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels, up2
 from ..schemas import generator_schema
 from ..window_index import padded_grid, token_grid
 from .modules.sparse_transformer import WIN, TransformerExec
@@ -66,26 +66,25 @@ class InpaintGenerator(ParamNet):
     # ------------------------------------------------------------------ conv trunk
     def _encoder(self, x):
         """Encoder.forward propainter.py:218-232; x [n,8,H,W] channels_last (5 real + 3 zero channels)."""
-        out = _lrelu(conv(x, self._wb("encoder.layers.0", 8), 2, 1))
-        out = _lrelu(conv(out, self._wb("encoder.layers.2"), 1, 1))
-        out = _lrelu(conv(out, self._wb("encoder.layers.4"), 2, 1))
-        out = _lrelu(conv(out, self._wb("encoder.layers.6"), 1, 1))
+        L = dict(act="leaky", slope=0.2)
+        out = conv(x, self._wb("encoder.layers.0", 8), 2, 1, **L)
+        out = conv(out, self._wb("encoder.layers.2"), 1, 1, **L)
+        out = conv(out, self._wb("encoder.layers.4"), 2, 1, **L)
+        out = conv(out, self._wb("encoder.layers.6"), 1, 1, **L)
         x0 = as_pm(out)                                                       # [n,h,w,256]
         n, h, w, _ = x0.shape
-        out = _lrelu(conv(out, self._wb("encoder.layers.8"), 1, 1))
+        out = conv(out, self._wb("encoder.layers.8"), 1, 1, **L)
         for i, g in ((10, 2), (12, 4), (14, 8), (16, 1)):
             o = as_pm(out)
             mix = torch.cat([x0.view(n, h, w, g, -1), o.view(n, h, w, g, -1)], -1).view(n, h, w, -1)   # group-wise skip
-            out = _lrelu(conv(as_nchw(mix), self._wb(f"encoder.layers.{i}"), 1, 1, 1, g))
+            out = conv(as_nchw(mix), self._wb(f"encoder.layers.{i}"), 1, 1, 1, g, **L)
         return out
 
-    def _up2_conv(self, key, x):
-        return conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True), self._wb(key + ".conv"), 1, 1)
-
     def _decoder(self, x):
-        x = _lrelu(self._up2_conv("decoder.0", x))
-        x = _lrelu(conv(x, self._wb("decoder.2"), 1, 1))
-        x = _lrelu(self._up2_conv("decoder.4", x))
+        L = dict(act="leaky", slope=0.2)
+        x = conv(up2(x), self._wb("decoder.0.conv"), 1, 1, **L)
+        x = conv(x, self._wb("decoder.2"), 1, 1, **L)
+        x = conv(up2(x), self._wb("decoder.4.conv"), 1, 1, **L)
         return conv(x, self._wb("decoder.6"), 1, 1)
 
     # ------------------------------------------------------------------ learnable feature propagation
@@ -114,22 +113,51 @@ class InpaintGenerator(ParamNet):
                     fprop, fchk = (dsf[idx], dsb[idx]) if bwd else (dsb[idx - 1], dsf[idx - 1])
                     ops.prop_cond(src[idx], prev, fprop, fchk, pmask[idx], cond[0], bb[0], False)
                     p = f"{fp}deform_align.{name}.conv_offset."
-                    o = F.leaky_relu_(conv(as_nchw(cond), self._wb(p + "0", 2 * C + 8), 1, 1), 0.1)
-                    o = F.leaky_relu_(conv(o, self._wb(p + "2"), 1, 1), 0.1)
-                    o = F.leaky_relu_(conv(o, self._wb(p + "4"), 1, 1), 0.1)
+                    o = conv(as_nchw(cond), self._wb(p + "0", 2 * C + 8), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._wb(p + "2"), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._wb(p + "4"), 1, 1, act="leaky", slope=0.1)
                     o = as_pm(conv(o, self._wb(p + "6"), 1, 1))
                     ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C])
-                y = conv(_lrelu(conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1)),
+                y = conv(conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2),
                          self._wb(f"{fp}backbone.{name}.2"), 1, 1)
                 torch.add(bb[0, :, :, C:2 * C], as_pm(y)[0], out=dst[idx])
                 prev = dst[idx]
             outs[name] = dst
             src = dst                                            # forward scan consumes the backward features (:138)
         z = torch.cat([outs["backward_1"], outs["forward_1"], pmask, pmask.new_zeros(lt, h, w, 2)], -1)
-        z = conv(_lrelu(conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1)), self._wb(fp + "fuse.2"), 1, 1)
+        z = conv(conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2), self._wb(fp + "fuse.2"), 1, 1)
         return z + as_nchw(x)
 
     # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def encode(self, masked_frames, masks_in, masks_updated, chunk=40):
+        """Encoder features of a set of frames: [n,3,H,W], [n,1,H,W], [n,1,H,W] -> [n,128,H/4,W/4].
+        The encoder output of a frame depends only on (frame, mask_in, mask_updated), so the sliding-window
+        driver calls this once per clip and feeds ``forward_features``; the reference re-encodes every frame
+        in each of the ~3.5 windows that select it (propainter.py:330-333, 58 % of the generator's conv FLOPs)."""
+        outs = []
+        for s in range(0, masked_frames.shape[0], chunk):
+            outs.append(self.graphs("gen_enc", self._encode_frames, masked_frames[s:s + chunk].contiguous().float(),
+                                    masks_in[s:s + chunk].contiguous().float(), masks_updated[s:s + chunk].contiguous().float()))
+        return torch.cat(outs, 0)
+
+    def _encode_frames(self, fr, mi, mu):
+        n, _, H, W = fr.shape
+        x = torch.cat([fr, mi, mu, fr.new_zeros(n, 3, H, W)], 1).contiguous(memory_format=torch.channels_last)
+        return self._encoder(x).contiguous(memory_format=torch.channels_last)
+
+    @torch.no_grad()
+    def forward_features(self, enc_feat, completed_flows, masks_in, masks_updated, num_local_frames,
+                         interpolation="bilinear", t_dilation=2):
+        """``forward`` minus the encoder: enc_feat [t,128,h,w] (local frames first), flows 2x[lt-1,2,H,W],
+        masks [t,1,H,W] -> [lt,3,H,W]."""
+        lt = num_local_frames
+        return self.graphs(("gen_feat", lt, interpolation, t_dilation),
+                           lambda *a: self._forward_features(*a, lt, interpolation, t_dilation),
+                           enc_feat.contiguous(memory_format=torch.channels_last), completed_flows[0].contiguous().float(),
+                           completed_flows[1].contiguous().float(), masks_in.contiguous().float(),
+                           masks_updated.contiguous().float())
+
     @torch.no_grad()
     def forward(self, masked_frames, completed_flows, masks_in, masks_updated, num_local_frames,
                 interpolation="bilinear", t_dilation=2):
@@ -141,22 +169,22 @@ class InpaintGenerator(ParamNet):
             raise ValueError("H and W must be multiples of 8 (inference_propainter.py:34-45)")
         res = []
         for bi in range(b):
-            fr, mi, mu = masked_frames[bi].float(), masks_in[bi].float(), masks_updated[bi].float()
-            x = torch.cat([fr, mi, mu, fr.new_zeros(t, 3, H, W)], 1).contiguous(memory_format=torch.channels_last)
-            enc = self._encoder(x)                                                  # [t,128,h,w]
-            h, w = enc.shape[-2:]
-            dsf, dsb, pmask = ops.gen_prep(completed_flows[0][bi].contiguous().float(),
-                                           completed_flows[1][bi].contiguous().float(),
-                                           mi.contiguous(), mu.contiguous(), lt)
-            fh, fw = token_grid((h, w))
-            H2, W2 = padded_grid(fh, fw, WIN)
-            flags = ops.window_mask(pmask, fh, fw, H2 // WIN[0], W2 // WIN[1])
-            enc_pm = as_pm(enc)
-            local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
-            enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
-            tok = self.tx.soft_split(enc2)
-            tok = self.tx.run(tok, (h, w), flags, t_dilation)
-            enc3 = enc2 + self.tx.soft_comp(tok, (h, w))
-            out = torch.tanh(self._decoder(enc3[:lt]))
-            res.append(out.contiguous())
+            enc = self.encode(masked_frames[bi], masks_in[bi], masks_updated[bi])
+            res.append(self.forward_features(enc, (completed_flows[0][bi], completed_flows[1][bi]), masks_in[bi],
+                                             masks_updated[bi], lt, interpolation, t_dilation))
         return torch.stack(res, 0).view(b, lt, 3, H, W)
+
+    def _forward_features(self, enc, flows_f, flows_b, mi, mu, lt, interpolation, t_dilation):
+        """one window after the encoder; captured as one CUDA graph per shape signature."""
+        h, w = enc.shape[-2:]
+        dsf, dsb, pmask = ops.gen_prep(flows_f, flows_b, mi, mu, lt)
+        fh, fw = token_grid((h, w))
+        H2, W2 = padded_grid(fh, fw, WIN)
+        flags = ops.window_mask(pmask, fh, fw, H2 // WIN[0], W2 // WIN[1])
+        enc_pm = as_pm(enc)
+        local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
+        enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
+        tok = self.tx.soft_split(enc2)
+        tok = self.tx.run(tok, (h, w), flags, t_dilation)
+        enc3 = enc2 + self.tx.soft_comp(tok, (h, w))
+        return torch.tanh(self._decoder(enc3[:lt])).contiguous()

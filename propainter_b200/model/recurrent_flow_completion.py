@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from .._params import ParamNet
-from ..nn_util import as_nchw, as_pm, cl, conv
+from ..nn_util import as_nchw, as_pm, cl, conv, up2
 from ..schemas import rfc_schema
 
 
@@ -63,16 +63,16 @@ class RecurrentFlowCompleteNet(ParamNet):
         return self.packed("dcn:" + name, build)
 
     # ------------------------------------------------------------------ blocks
-    def _p3d(self, p, x, stride):
+    def _p3d(self, p, x, stride, act="leaky"):
         """P3DBlock :148-169 on a frame batch x [t,c,h,w] (channels_last)."""
-        y = _lrelu(conv(x, self._w2d(p + ".conv1.0"), stride, 1))
+        y = conv(x, self._w2d(p + ".conv1.0"), stride, 1, act="leaky", slope=0.2)
         t = y.shape[0]
         yp = F.pad(y, (0, 0, 0, 0, 0, 0, 2, 2))                             # zero-pad time by 2 (padding=(2,0,0))
         z = torch.cat([yp[0:t], yp[2:t + 2], yp[4:t + 4]], 1)                # dilation 2 taps
-        return conv(z, self._wt(p + ".conv2.0"))
+        return conv(z, self._wt(p + ".conv2.0"), act=act, slope=0.2)
 
-    def _up2_conv(self, key, x):
-        return conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True), self._w2d(key + ".conv"), 1, 1)
+    def _up2_conv(self, key, x, act="none"):
+        return conv(up2(x), self._w2d(key + ".conv"), 1, 1, act=act, slope=0.2)
 
     def _propagate(self, x):
         """BidirectionalPropagation.forward :67-124.  x [t,128,h,w] channels_last -> same."""
@@ -91,16 +91,16 @@ class RecurrentFlowCompleteNet(ParamNet):
                 if i > 0:
                     n2 = hist[i:i + 1]                                        # state of step i-2 (zeros for i=1)
                     buf = torch.cat([prop, n2, cur], -1)                      # [1,h,w,384] = deform input | cur
-                    o = _lrelu(conv(as_nchw(buf), self._offset_w0(name), 1, 1), 0.1)
-                    o = _lrelu(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1), 0.1)
-                    o = _lrelu(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1), 0.1)
+                    o = conv(as_nchw(buf), self._offset_w0(name), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1, act="leaky", slope=0.1)
                     o = as_pm(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.6"), 1, 1))
                     aligned = torch.empty(1, h, w, c, device=dev)
                     ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, aligned[0])
                     prop = aligned
                 parts = [cur] + ([results["backward_"][idx:idx + 1]] if di == 1 else []) + [prop]
                 f = as_nchw(torch.cat(parts, -1))
-                y = conv(_lrelu(conv(f, self._w2d(f"{fp}backbone.{name}.0"), 1, 1), 0.1),
+                y = conv(conv(f, self._w2d(f"{fp}backbone.{name}.0"), 1, 1, act="leaky", slope=0.1),
                          self._w2d(f"{fp}backbone.{name}.2"), 1, 1)
                 hist[i + 2] = prop[0] + as_pm(y)[0]
             seq = hist[2:]
@@ -113,24 +113,28 @@ class RecurrentFlowCompleteNet(ParamNet):
     def forward(self, masked_flows, masks):
         """:272-309 (eval).  masked_flows [b,t,2,h,w], masks [b,t,1,h,w] -> (flow [b,t,2,h,w], None)."""
         b, t, _, h, w = masked_flows.shape
-        outs = []
-        for bi in range(b):
-            x = torch.cat([masked_flows[bi], masks[bi]], 1)                          # [t,3,h,w]
+        outs = [self.graphs("rfc", self._forward_one, masked_flows[bi].contiguous().float(), masks[bi].contiguous().float())
+                for bi in range(b)]
+        return torch.stack(outs, 0).view(b, t, 2, h, w), None
+
+    def _forward_one(self, flows, masks):
+        """one clip: flows [t,2,h,w], masks [t,1,h,w] -> [t,2,h,w]; captured as a CUDA graph per shape."""
+        if True:
+            x = torch.cat([flows, masks], 1)                                         # [t,3,h,w]
             x = F.pad(x, (2, 2, 2, 2), mode="replicate").contiguous(memory_format=torch.channels_last)
-            x = _lrelu(conv(x, self._w2d("downsample.0"), 2, 0))
-            e1 = _lrelu(self._p3d("encoder1.0", x, 1))
-            e1 = _lrelu(self._p3d("encoder1.2", e1, 2))
-            e2 = _lrelu(self._p3d("encoder2.0", e1, 1))
-            e2 = _lrelu(self._p3d("encoder2.2", e2, 2))
+            x = conv(x, self._w2d("downsample.0"), 2, 0, act="leaky", slope=0.2)
+            e1 = self._p3d("encoder1.0", x, 1)
+            e1 = self._p3d("encoder1.2", e1, 2)
+            e2 = self._p3d("encoder2.0", e1, 1)
+            e2 = self._p3d("encoder2.2", e2, 2)
             m = e2
             for i, d in ((0, 3), (2, 2), (4, 1)):
-                m = _lrelu(conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d))
+                m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
             fpr = self._propagate(m)
-            d2 = _lrelu(self._up2_conv("decoder2.2", _lrelu(conv(fpr, self._w2d("decoder2.0"), 1, 1)))) + e1
-            d1 = _lrelu(self._up2_conv("decoder1.2", _lrelu(conv(d2, self._w2d("decoder1.0"), 1, 1))))
-            fl = self._up2_conv("upsample.2", _lrelu(conv(d1, self._w2d("upsample.0"), 1, 1)))
-            outs.append(fl.contiguous())
-        return torch.stack(outs, 0).view(b, t, 2, h, w), None
+            d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky") + e1
+            d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
+            fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
+            return fl.contiguous()
 
     @torch.no_grad()
     def forward_bidirect_flow(self, masked_flows_bi, masks):

@@ -80,13 +80,13 @@ def corr_build(fmap, idx1, idx2, levels, h, w):
     _count(4)
 
 
-def corr_lookup(levels, coords, out=None):
-    """coords [B,h,w,2] -> [B,h,w,324]."""
+def corr_lookup(levels, coords, out=None, tma=True):
+    """coords [B,h,w,2] -> [B,h,w,324].  tma=False selects the plain-load baseline kernel."""
     B, h, w, _ = coords.shape
     if out is None:
         out = torch.empty(B, h, w, 324, device=coords.device, dtype=torch.float32)
-    check(_lib.lib().pp_corr_lookup(_level_array(levels), _p(_dense(coords)), _p(_dense(out)), B, h, w, _stream()),
-          "pp_corr_lookup")
+    fn = _lib.lib().pp_corr_lookup if tma else _lib.lib().pp_corr_lookup_ldg
+    check(fn(_level_array(levels), _p(_dense(coords)), _p(_dense(out)), B, h, w, _stream()), "pp_corr_lookup")
     _count(1)
     return out
 
@@ -197,6 +197,27 @@ def ffn_overlap_add(Y, frames, h, w, CH=40):
                                _stream()), "pp_ffn_overlap_add")
     _count(2)
     return Z
+
+
+ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
+
+
+def bias_act_(x_pm, bias, act="none", slope=0.0):
+    """in-place act(x + bias) on a dense pixel-major tensor [..., C]; returns x_pm."""
+    C = x_pm.shape[-1]
+    check(_lib.lib().pp_bias_act(_p(_dense(x_pm)), _p(_dense(bias)), x_pm.numel() // C, C, ACT[act], float(slope), _stream()),
+          "pp_bias_act")
+    _count(1)
+    return x_pm
+
+
+def upsample2x(x_pm):
+    """pixel-major [n,h,w,C] -> [n,2h,2w,C], bilinear, align_corners=True."""
+    n, h, w, C = x_pm.shape
+    out = torch.empty(n, 2 * h, 2 * w, C, device=x_pm.device, dtype=torch.float32)
+    check(_lib.lib().pp_upsample2x_bilinear(_p(_dense(x_pm)), _p(out), n, h, w, C, _stream()), "pp_upsample2x_bilinear")
+    _count(1)
+    return out
 
 
 def u8_to_frames(frames_u8):

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (runs on the B200 box)")
+    config.addinivalue_line("markers", "shipping: run with the default (benchmarked) precision switches")
 
 
 @pytest.fixture(scope="session")

@@ -156,3 +156,17 @@ void hs_composite(const float* pred, const float* masks, const uint8_t* ori, uin
       }
 }
 }
+
+extern "C" void hs_upsample2x(const float* src, float* dst, int n, int h, int w, int C) {
+  const int H = 2 * h, W = 2 * w;
+  for (int b = 0; b < n; ++b)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        PPUp uy = pp_up2_coord(y, h), ux = pp_up2_coord(x, w);
+        for (int c = 0; c < C; ++c) {
+          const float* p = src + (((long)b * h + uy.i0) * w + ux.i0) * C + c;
+          dst[(((long)b * H + y) * W + x) * C + c] =
+              pp_up2_blend(p[0], p[(long)ux.step * C], p[(long)uy.step * w * C], p[((long)uy.step * w + ux.step) * C], uy, ux);
+        }
+      }
+}

@@ -135,6 +135,19 @@ def install(monkeypatch, hostsim):
         hostsim.hs_composite(_fp(p), _fp(m), ctypes.c_void_p(ori_u8.data_ptr()), ctypes.c_void_p(comp_u8.data_ptr()), n, fr,
                              fs, H, W)
 
+    def bias_act_(x_pm, bias, act="none", slope=0.0):
+        x_pm.add_(bias)
+        {"none": lambda: None, "relu": lambda: F.relu_(x_pm), "leaky": lambda: F.leaky_relu_(x_pm, slope),
+         "sigmoid": lambda: torch.sigmoid_(x_pm), "tanh": lambda: torch.tanh_(x_pm)}[act]()
+        return x_pm
+
+    def upsample2x(x_pm):
+        n, h, w, C = x_pm.shape
+        x_pm = x_pm.contiguous()
+        out = torch.empty(n, 2 * h, 2 * w, C)
+        hostsim.hs_upsample2x(_fp(x_pm), _fp(out), n, h, w, C)
+        return out
+
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name) and not name.startswith("_"):
             monkeypatch.setattr(ops, name, fn)

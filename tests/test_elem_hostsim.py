@@ -192,3 +192,14 @@ def test_u8_and_composite(hostsim):
         hostsim.hs_composite(fp(pred), fp(masks), ctypes.c_void_p(u8.data_ptr()), ctypes.c_void_p(comp.data_ptr()),
                              len(ids), fr, fs, H, W)
     assert np.array_equal(comp.numpy(), np.stack(ref, 0))
+
+
+def test_upsample2x(hostsim):
+    gen = torch.Generator().manual_seed(9)
+    for (n, h, w, C) in ((2, 15, 27, 8), (1, 30, 54, 4)):
+        x = torch.randn(n, C, h, w, generator=gen)
+        ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        xp = x.permute(0, 2, 3, 1).contiguous()
+        out = torch.empty(n, 2 * h, 2 * w, C)
+        hostsim.hs_upsample2x(fp(xp), fp(out), n, h, w, C)
+        assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-6, rtol=1e-6)

@@ -20,12 +20,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(autouse=True)
-def _exact_library_math():
-    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+def _exact_library_math(request):
+    """fp32 library convs / GEMMs (isolates our kernels) -- except for tests marked `shipping`, which run the
+    defaults bench.py runs: cuDNN TF32 convs (torch default) + TF32 Linear GEMMs (config.LINEAR_TF32)."""
+    from propainter_b200 import config
+    if "shipping" in request.keywords:
+        yield
+        return
+    a, b, c = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, config.LINEAR_TF32
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    config.LINEAR_TF32 = False
     yield
-    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, config.LINEAR_TF32 = a, b, c
 
 
 def cpu_sd(m):
@@ -147,3 +154,21 @@ def test_pipeline_chunked_long_clip():
     psnr = ops_ref.psnr_u8(comp, ref)
     print(f"chunked: PSNR {psnr:.2f} dB")
     assert psnr > 38.0
+
+
+@pytest.mark.shipping
+def test_pipeline_shipping_defaults_vs_golden_and_oracle():
+    """Defaults exactly as benchmarked (TF32 convs + TF32 linears + CUDA graphs): final video vs the committed
+    golden output of the reference modules, and replay determinism of the captured graphs."""
+    from propainter_b200 import synth
+    from propainter_b200.inference_propainter import InferenceConfig, ProPainterPipeline
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_8x128x128_square_it6.npz"))
+    u8, fm, md = synth.make_clip(8, 128, 128, mask="square", seed=0)
+    pipe = ProPainterPipeline(device=DEV)
+    cfg = InferenceConfig(raft_iter=6)
+    a = pipe(torch.from_numpy(u8), fm, md, cfg).cpu().numpy()
+    b = pipe(torch.from_numpy(u8), fm, md, cfg).cpu().numpy()          # second call replays the captured graphs
+    assert np.array_equal(a, b)
+    psnr = ops_ref.psnr_u8(a, g["comp"])
+    print(f"shipping defaults vs reference golden: PSNR {psnr:.2f} dB, max diff {np.abs(a.astype(int) - g['comp'].astype(int)).max()}")
+    assert psnr > 40.0

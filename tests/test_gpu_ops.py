@@ -27,6 +27,7 @@ def _exact_library_math():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
 
 
+
 def smooth_flow(gen, n, H, W, amp=4.0):
     z = torch.randn(n, 2, H // 8 + 2, W // 8 + 2, generator=gen) * amp
     return F.interpolate(z, size=(H, W), mode="bicubic", align_corners=False).contiguous()
@@ -96,8 +97,15 @@ def test_corr_build_pool_lookup():
         ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
         coords = torch.stack([xs, ys], 0).float()[None].repeat(B, 1, 1, 1) + torch.randn(B, 2, h, w, generator=gen) * 6
         ref = ops_ref.corr_lookup(pyr, coords)
-        got = ops.corr_lookup(levels, coords.permute(0, 2, 3, 1).contiguous().to(DEV)).cpu().permute(0, 3, 1, 2)
-        assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+        cpm = coords.permute(0, 2, 3, 1).contiguous().to(DEV)
+        for tma in (True, False):
+            got = ops.corr_lookup(levels, cpm, tma=tma).cpu().permute(0, 3, 1, 2)
+            assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (tma, (got - ref).abs().max())
+        far = cpm.clone()
+        far[0, :2] += 500.0                      # centres far outside the image -> all-zero windows, no faults
+        far[1, :2] -= 500.0
+        a, b = ops.corr_lookup(levels, far, tma=True), ops.corr_lookup(levels, far, tma=False)
+        assert torch.equal(a, b) and (a[0, :2] == 0).all() and (a[1, :2] == 0).all()
 
 
 def test_convex_upsample():
@@ -221,6 +229,23 @@ def test_ffn_overlap_add():
         perm = torch.arange(49 * CH).view(CH, 49).t().reshape(-1)
         Z = ops.ffn_overlap_add(Y[:, perm].contiguous().to(DEV), frames, h, w, CH).cpu()
         assert torch.allclose(Z, ref[:, perm], atol=1e-5, rtol=1e-5)
+
+
+def test_bias_act_and_upsample2x():
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(3, 17, 23, 64, generator=gen)
+    b = torch.randn(64, generator=gen)
+    refs = {"none": x + b, "relu": F.relu(x + b), "leaky": F.leaky_relu(x + b, 0.1), "sigmoid": torch.sigmoid(x + b),
+            "tanh": torch.tanh(x + b)}
+    for act, ref in refs.items():
+        got = ops.bias_act_(x.clone().to(DEV), b.to(DEV), act, 0.1).cpu()
+        assert torch.allclose(got, ref, atol=2e-6, rtol=1e-6), act
+    for (n, h, w, C) in ((2, 30, 54, 128), (1, 15, 27, 32)):
+        z = torch.randn(n, C, h, w, generator=gen)
+        ref = F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=True)
+        got = ops.upsample2x(z.permute(0, 2, 3, 1).contiguous().to(DEV)).cpu().permute(0, 3, 1, 2)
+        assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
 
 
 def test_u8_and_composite():
