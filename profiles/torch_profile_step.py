@@ -35,7 +35,7 @@ with torch.no_grad():
     timed("4 generator+composite", lambda: pipe.generate(upd[0], mdd, upd[1], pred, u8d, cfg))
 print("stage ms:", {k: round(v, 2) for k, v in stage_ms.items()})
 from torch.profiler import ProfilerActivity, profile
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
     pipe(u8d, fmd, mdd, cfg)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))

@@ -2,7 +2,9 @@
 //
 // One warp per source pixel.  For each of the 4 pyramid levels the warp's elected lane issues one
 // cp.async.bulk.tensor (TMA, 3-D tiled: x, y, plane) that lands the 12x12 neighbourhood of the lookup
-// centre in shared memory; out-of-range rows / columns are zero-filled by the TMA unit, which *is*
+// centre in shared memory (the box's innermost coordinate is rounded down to a multiple of 4 floats: a
+// tiled TMA load whose first element is not 16-byte aligned faults with "illegal instruction" -- measured
+// with profiles/probes/tma_probe.cu); out-of-range rows / columns are zero-filled by the TMA unit, which *is*
 // grid_sample's zeros padding, so the inner loop has no bounds logic on loads.  The 81 taps of a level
 // are then bilinear blends of shared-memory values and are written as one contiguous 324-float run.
 // Replaces CorrBlock.__call__ (RAFT/corr.py:29-50) + bilinear_sampler (RAFT/utils/utils.py:57-71).
@@ -11,9 +13,10 @@
 #include "../../include/propainter_b200.h"
 
 #define LK_WARPS 8
-#define LK_BOX 12
+#define LK_BOX 12                       // rows of the staged box
+#define LK_BOXW 16                      // columns: 12 needed + up to 3 because the box must start 16-byte aligned
 #define LK_HALF 5
-#define LK_LVL_FLOATS 160               // 12*12 = 144 floats, padded to 640 B so every box is 128-byte aligned
+#define LK_LVL_FLOATS (LK_BOX * LK_BOXW) // 768 B per level: every box stays 128-byte aligned in shared memory
 
 __device__ __forceinline__ uint32_t lk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -36,11 +39,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_
   const uint32_t bar_a = lk_smem(&bar[warp]);
   int bx[4], by[4];
 #pragma unroll
-  for (int l = 0; l < 4; ++l) { bx[l] = lk_base(cx, 1.0f / (float)(1 << l)); by[l] = lk_base(cy, 1.0f / (float)(1 << l)); }
+  for (int l = 0; l < 4; ++l) { bx[l] = lk_base(cx, 1.0f / (float)(1 << l)) & ~3; by[l] = lk_base(cy, 1.0f / (float)(1 << l)); }
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_BOX * LK_BOX * 4) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_LVL_FLOATS * 4) : "memory");
     const CUtensorMap* tms[4] = {&tm0, &tm1, &tm2, &tm3};
 #pragma unroll
     for (int l = 0; l < 4; ++l)
@@ -69,9 +72,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_
       float v = 0.f;
       if (t.any) {
         const int px = t.x0 - bx[l], py = t.y0 - by[l];          // position inside the staged box
-        if (px >= 0 && px + 1 < LK_BOX && py >= 0 && py + 1 < LK_BOX) {
-          const float* q = P + py * LK_BOX + px;
-          v = q[0] * t.w00 + q[1] * t.w01 + q[LK_BOX] * t.w10 + q[LK_BOX + 1] * t.w11;
+        if (px >= 0 && px + 1 < LK_BOXW && py >= 0 && py + 1 < LK_BOX) {
+          const float* q = P + py * LK_BOXW + px;
+          v = q[0] * t.w00 + q[1] * t.w01 + q[LK_BOXW] * t.w10 + q[LK_BOXW + 1] * t.w11;
         }
       }
       o[l * 81 + tap] = v;
@@ -106,7 +109,7 @@ extern "C" int pp_corr_lookup(const float* const* levels, const float* coords, f
     const int ld = pp_corr_ld(wl);
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)hl, (cuuint64_t)npix};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)hl * ld * 4};
-    cuuint32_t box[3] = {LK_BOX, LK_BOX, 1};
+    cuuint32_t box[3] = {LK_BOXW, LK_BOX, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (((uintptr_t)levels[l] & 15) != 0) return PP_ERR_ALIGN;
     CUresult r = enc(&tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)levels[l], dims, strides, box, estr,
