@@ -97,6 +97,18 @@ size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH);
 int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH, void* workspace,
                        size_t ws_bytes, cudaStream_t stream);
 
+/* ---- RAFT SepConvGRU elementwise fusion (RAFT/update.py:45-60,95-97) ------------------------- */
+/* zr: raw output of the fused z|r gate conv [npix][2C]; net: state slice of HX (ld_net); writes z [npix][C]
+ * and r*net into the state slice of RX (ld_r). */
+int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet, int ld_r,
+                long npix, int C, cudaStream_t stream);
+/* net = (1-z)*net + z*tanh(q + bias), in place on the state slice of HX. */
+int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, long npix, int C,
+                  cudaStream_t stream);
+/* motion features: channels [0,126) of `mot` + the 2 flow channels -> the same 128-channel slot of d0 and d1. */
+int pp_raft_pack_motion(const float* mot, int ld_mot, const float* flow, float* d0, float* d1, int ld, long npix,
+                        cudaStream_t stream);
+
 /* ---- conv epilogues ------------------------------------------------------------------------- */
 /* In-place y = act(x + bias[c]) on a dense pixel-major tensor [n_pix][C]: replaces the bias add of
  * F.conv2d plus the ReLU / LeakyReLU / sigmoid / tanh that follows it at every conv of the three nets.

@@ -44,6 +44,15 @@ class RAFT(ParamNet):
             return cl(w), b.contiguous()
         return self.packed("wb:" + key, build)
 
+    def _motion_out(self):
+        """update_block.encoder.conv with its 126 outputs padded to 128 (two zero filters): keeps the output
+        rows 16-byte aligned; the pad slots are overwritten by the flow channels in raft_pack_motion."""
+        def build():
+            w, b = self.P["update_block.encoder.conv.weight"], self.P["update_block.encoder.conv.bias"]
+            w = torch.cat([w, w.new_zeros(2, *w.shape[1:])], 0)
+            return cl(w), torch.cat([b, b.new_zeros(2)]).contiguous()
+        return self.packed("motion_out", build)
+
     def _gates(self, tag):
         def build():
             u = "update_block.gru."
@@ -95,25 +104,32 @@ class RAFT(ParamNet):
         c1 = c0.clone()
         if flow_init is not None:
             c1 = c1 + as_pm(flow_init)
-        net = net.contiguous(memory_format=torch.channels_last)
-        inp = inp.contiguous(memory_format=torch.channels_last)
         u = "update_block."
         corr = torch.empty(B, h, w, 324, device=dev)
+        # persistent GRU buffers (no torch.cat inside the loop):
+        #   HX = [net | inp | motion(126) flow(2)]  -> z/r gate convs;   RX = [r*net | inp | motion flow] -> candidate conv
+        HX = torch.empty(B, h, w, 384, device=dev)
+        RX = torch.empty(B, h, w, 384, device=dev)
+        HX[..., :128] = as_pm(net)
+        HX[..., 128:256] = as_pm(inp)
+        RX[..., 128:256] = HX[..., 128:256]
+        netv, z = HX[..., :128], torch.empty(B, h, w, 128, device=dev)
         for _ in range(iters):
             ops.corr_lookup(levels, c1, corr)
-            flow = as_nchw(c1 - c0)
+            flow_pm = c1 - c0
+            flow = as_nchw(flow_pm)
             cor = conv(as_nchw(corr), self._wb(u + "encoder.convc1"), act="relu")
             cor = conv(cor, self._wb(u + "encoder.convc2"), 1, 1, act="relu")
             flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
             flo = conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu")
-            mot = conv(torch.cat([cor, flo], 1), self._wb(u + "encoder.conv"), 1, 1, act="relu")
-            x = torch.cat([inp, mot, flow], 1)
+            mot = conv(torch.cat([cor, flo], 1), self._motion_out(), 1, 1, act="relu")          # 126 real + 2 pad channels
+            ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 256:], RX[..., 256:])
             for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
-                hx = torch.cat([net, x], 1)
-                zr = conv(hx, self._gates(tag), 1, pad, act="sigmoid")
-                z, r = zr[:, :128], zr[:, 128:]
-                q = conv(torch.cat([r * net, x], 1), self._wb(u + f"gru.convq{tag}"), 1, pad, act="tanh")
-                net = torch.lerp(net, q, z)                     # (1-z)*h + z*q
+                gw, gb = self._gates(tag)
+                qw, qb = self._wb(u + f"gru.convq{tag}")
+                ops.gru_gate(as_pm(F.conv2d(as_nchw(HX), gw, None, padding=pad)), gb, netv, z, RX[..., :128])
+                ops.gru_update(as_pm(F.conv2d(as_nchw(RX), qw, None, padding=pad)), qb, z, netv)
+            net = as_nchw(netv.contiguous())
             d = conv(conv(net, self._wb(u + "flow_head.conv1"), 1, 1, act="relu"), self._wb(u + "flow_head.conv2"), 1, 1)
             c1 = c1 + as_pm(d)
         flow_lr = c1 - c0

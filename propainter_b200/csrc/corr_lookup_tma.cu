@@ -60,26 +60,25 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_
     if (!done) __trap();
   }
   float* o = out + pix * 324;
-  int hl = h, wl = w;
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
+    // All 81 taps of a level share the fractional part of the centre (integer tap offsets), so the
+    // weights are computed once; corners outside the image read the zeros TMA filled in.  (The reference
+    // sends each tap through grid_sample's normalise/un-normalise round trip, RAFT/utils/utils.py:60-65,
+    // which only adds ~1e-6 px of rounding noise -- dropped here, well inside the 1e-4 parity tolerance.)
     const float* P = &patch[warp][l][0];
-    const float s = (float)(1 << l);
-    const float xl = PP_DIV(cx, s), yl = PP_DIV(cy, s);
+    const float inv = 1.0f / (float)(1 << l);
+    const float xl = cx * inv, yl = cy * inv;
+    const float fxl = floorf(xl), fyl = floorf(yl);
+    const bool sane = fabsf(xl) < 1.0e6f && fabsf(yl) < 1.0e6f;
+    const float wx1 = sane ? xl - fxl : 0.f, wy1 = sane ? yl - fyl : 0.f;
+    const float wx0 = sane ? 1.0f - wx1 : 0.f, wy0 = sane ? 1.0f - wy1 : 0.f;
+    const int ox = lk_base(cx, inv) + 1 - bx[l], oy = 1;        // box position of tap (0,0)'s top-left corner
     for (int tap = lane; tap < 81; tap += 32) {
-      const int a = tap / 9, b = tap - a * 9;
-      const PPTaps t = pp_taps(pp_raft_coord(PP_ADD(xl, (float)(a - 4)), wl), pp_raft_coord(PP_ADD(yl, (float)(b - 4)), hl), hl, wl);
-      float v = 0.f;
-      if (t.any) {
-        const int px = t.x0 - bx[l], py = t.y0 - by[l];          // position inside the staged box
-        if (px >= 0 && px + 1 < LK_BOXW && py >= 0 && py + 1 < LK_BOX) {
-          const float* q = P + py * LK_BOXW + px;
-          v = q[0] * t.w00 + q[1] * t.w01 + q[LK_BOXW] * t.w10 + q[LK_BOXW + 1] * t.w11;
-        }
-      }
-      o[l * 81 + tap] = v;
+      const int a = tap / 9, b = tap - a * 9;                    // a moves x, b moves y (RAFT/corr.py:38-44)
+      const float* q = P + (oy + b) * LK_BOXW + ox + a;
+      o[l * 81 + tap] = wy0 * (wx0 * q[0] + wx1 * q[1]) + wy1 * (wx0 * q[LK_BOXW] + wx1 * q[LK_BOXW + 1]);
     }
-    hl >>= 1; wl >>= 1;
   }
 }
 

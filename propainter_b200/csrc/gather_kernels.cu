@@ -371,6 +371,76 @@ extern "C" int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h
   return PP_OK;
 }
 
+// ================================================================ RAFT SepConvGRU elementwise fusion
+// RAFT/update.py:45-60.  The recurrent state lives in two persistent pixel-major buffers
+//   HX = [net | inp | motion | flow]   (input of the z/r gate conv)
+//   RX = [r*net | inp | motion | flow] (input of the candidate conv)
+// so no torch.cat is needed inside the 20-iteration loop.
+__global__ void __launch_bounds__(256) k_gru_gate(const float* __restrict__ zr, const float* __restrict__ bias,
+    const float* __restrict__ net, int ld_net, float* __restrict__ z, float* __restrict__ rnet, int ld_r, long npix, int C) {
+  const int c4n = C >> 2;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c4n) return;
+  const long pix = i / c4n; const int c = (int)(i - pix * c4n) * 4;
+  const float4 zv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + c), rv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + C + c);
+  const float4 bz = *reinterpret_cast<const float4*>(bias + c), br = *reinterpret_cast<const float4*>(bias + C + c);
+  const float4 h = *reinterpret_cast<const float4*>(net + pix * ld_net + c);
+  float4 zo, ro;
+  zo.x = 1.0f / (1.0f + expf(-(zv.x + bz.x))); zo.y = 1.0f / (1.0f + expf(-(zv.y + bz.y)));
+  zo.z = 1.0f / (1.0f + expf(-(zv.z + bz.z))); zo.w = 1.0f / (1.0f + expf(-(zv.w + bz.w)));
+  ro.x = h.x / (1.0f + expf(-(rv.x + br.x))); ro.y = h.y / (1.0f + expf(-(rv.y + br.y)));
+  ro.z = h.z / (1.0f + expf(-(rv.z + br.z))); ro.w = h.w / (1.0f + expf(-(rv.w + br.w)));
+  *reinterpret_cast<float4*>(z + pix * C + c) = zo;
+  *reinterpret_cast<float4*>(rnet + pix * ld_r + c) = ro;
+}
+__global__ void __launch_bounds__(256) k_gru_update(const float* __restrict__ q, const float* __restrict__ bias,
+    const float* __restrict__ z, float* __restrict__ net, int ld_net, long npix, int C) {
+  const int c4n = C >> 2;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * c4n) return;
+  const long pix = i / c4n; const int c = (int)(i - pix * c4n) * 4;
+  const float4 qv = *reinterpret_cast<const float4*>(q + pix * C + c), b = *reinterpret_cast<const float4*>(bias + c);
+  const float4 zv = *reinterpret_cast<const float4*>(z + pix * C + c);
+  float4 h = *reinterpret_cast<float4*>(net + pix * ld_net + c);
+  h.x = (1.0f - zv.x) * h.x + zv.x * tanhf(qv.x + b.x); h.y = (1.0f - zv.y) * h.y + zv.y * tanhf(qv.y + b.y);
+  h.z = (1.0f - zv.z) * h.z + zv.z * tanhf(qv.z + b.z); h.w = (1.0f - zv.w) * h.w + zv.w * tanhf(qv.w + b.w);
+  *reinterpret_cast<float4*>(net + pix * ld_net + c) = h;
+}
+// z = sigmoid(conv_z), r*h (update.py:47-49 / :54-56): zr = raw output of the fused z|r conv [npix][2C]
+extern "C" int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet,
+                           int ld_r, long npix, int C, cudaStream_t stream) {
+  if (C % 4 || ld_net % 4 || ld_r % 4) return PP_ERR_ALIGN;
+  k_gru_gate<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(zr, bias, net, ld_net, z, rnet, ld_r, npix, C);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+// h = (1-z)*h + z*tanh(conv_q) in place (update.py:50-51 / :57-58)
+extern "C" int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, long npix, int C,
+                             cudaStream_t stream) {
+  if (C % 4 || ld_net % 4) return PP_ERR_ALIGN;
+  k_gru_update<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(q, bias, z, net, ld_net, npix, C);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+// motion features [out(126) | flow(2)] (update.py:95-97) written into the same channel slot of two buffers
+__global__ void __launch_bounds__(256) k_raft_pack_motion(const float* __restrict__ mot, int ld_mot, const float* __restrict__ flow,
+    float* __restrict__ d0, float* __restrict__ d1, int ld, long npix) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // 32 float4 per pixel (128 channels)
+  if (i >= npix * 32) return;
+  const long pix = i >> 5; const int c = (int)(i & 31) * 4;
+  float4 v = *reinterpret_cast<const float4*>(mot + pix * ld_mot + c);
+  if (c == 124) { v.z = flow[2 * pix]; v.w = flow[2 * pix + 1]; }
+  *reinterpret_cast<float4*>(d0 + pix * ld + c) = v;
+  *reinterpret_cast<float4*>(d1 + pix * ld + c) = v;
+}
+extern "C" int pp_raft_pack_motion(const float* mot, int ld_mot, const float* flow, float* d0, float* d1, int ld, long npix,
+                                   cudaStream_t stream) {
+  if (ld % 4 || ld_mot % 4) return PP_ERR_ALIGN;
+  k_raft_pack_motion<<<pp_blocks(npix * 32, 256), 256, 0, stream>>>(mot, ld_mot, flow, d0, d1, ld, npix);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 // ================================================================ frame conversion + compositing
 __global__ void __launch_bounds__(256) k_u8_to_frames(const uint8_t* __restrict__ src, float* __restrict__ dst, int T,
                                                       int H, int W) {

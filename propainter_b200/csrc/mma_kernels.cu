@@ -101,11 +101,42 @@ extern "C" int pp_corr_build(const float* fmap, int D, const int* idx1, const in
 // CTA = 32 pixels x 128 outputs, 4 warps (2 along M x 2 along N).  Each K-step stages the modulated
 // bilinear samples of (tap k, 32 channels) for the 32 pixels into shared memory -- the im2col matrix
 // torchvision materialises in HBM never exists -- and the matching 32x128 weight slab via cp.async.
+// Two-stage software pipeline: while the tensor cores work on stage i, the weight slab of stage i+1 is
+// in flight (cp.async) and the gather's global loads for stage i+1 are already issued into registers.
+// Fragment loads are vectorised by renaming indices the MMA is indifferent to: inside each 8-wide
+// k-step logical k=t / t+4 live at physical 2t / 2t+1 (one LDS.64 for A, adjacent rows for B), and
+// the 8 n-tiles of a warp are interleaved (physical column 32q+4g+j <-> tile 4q+j, n=g) so that one
+// LDS.128 of B feeds four MMAs and the epilogue stores float4.
+#define DA_LDA 40
+#define DA_LDB 132
+struct DAGather { float4 s0, s1; };
+__device__ __forceinline__ DAGather da_gather(const float* __restrict__ x, int ld_x, const float* __restrict__ op,
+                                              const float* __restrict__ fp, float max_res, int H, int W, int cpg, int k,
+                                              int c, int y, int xx, bool valid) {
+  DAGather r;
+  r.s0 = make_float4(0.f, 0.f, 0.f, 0.f); r.s1 = r.s0;
+  if (!valid) return r;
+  const PPDTap tp = pp_deform_tap(op, fp, max_res, c / cpg, k, y, xx);
+  const PPDW d = pp_deform_weights(tp, H, W);
+  const float* p = x + ((long)d.y0 * W + d.x0) * ld_x + c;
+#define PP_DACC(ptr, wt)                                                                         \
+  if ((wt) != 0.f) { const float4 u = *reinterpret_cast<const float4*>(ptr);                    \
+    const float4 v = *reinterpret_cast<const float4*>((ptr) + 4);                               \
+    r.s0.x += u.x * (wt); r.s0.y += u.y * (wt); r.s0.z += u.z * (wt); r.s0.w += u.w * (wt);     \
+    r.s1.x += v.x * (wt); r.s1.y += v.y * (wt); r.s1.z += v.z * (wt); r.s1.w += v.w * (wt); }
+  PP_DACC(p, d.w00)
+  PP_DACC(p + ld_x, d.w01)
+  PP_DACC(p + (long)W * ld_x, d.w10)
+  PP_DACC(p + (long)W * ld_x + ld_x, d.w11)
+#undef PP_DACC
+  return r;
+}
+
 __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float* __restrict__ o,
     int ld_o, const float* __restrict__ flow, float max_res, const float* __restrict__ Wp,
     const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin) {
-  __shared__ __align__(16) float As[32][36];
-  __shared__ __align__(16) float Bs[32][136];
+  __shared__ __align__(16) float As[2][32][DA_LDA];
+  __shared__ __align__(16) float Bs[2][32][DA_LDB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int px_l = tid >> 2, cseg = tid & 3;
@@ -113,7 +144,7 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
   const long pix = (long)blockIdx.x * 32 + px_l;
   const bool valid = pix < npix;
   const int y = valid ? (int)(pix / W) : 0, xx = valid ? (int)(pix - (long)y * W) : 0;
-  const int cpg = Cin / 16;
+  const int cpg = Cin / 16, cblocks = Cin / 32, nit = 9 * cblocks;
   const float* op = o + (valid ? pix : 0) * ld_o;
   const float* fp = flow ? flow + 2 * (valid ? pix : 0) : nullptr;
   float acc[8][4];
@@ -122,60 +153,74 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 
-  for (int k = 0; k < 9; ++k) {
-    for (int c0 = 0; c0 < Cin; c0 += 32) {
-      __syncthreads();
+  auto load_b = [&](int it, int buf) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
-        pp_cp_async16(&Bs[row][c4 * 4], Wp + ((long)k * Cin + c0 + row) * 128 + c4 * 4);
-      }
-      pp_cp_async_commit();
-      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-      if (valid) {
-        const int c = c0 + cseg * 8;
-        PPDTap tp = pp_deform_tap(op, fp, max_res, c / cpg, k, y, xx);
-        PPDW d = pp_deform_weights(tp, H, W);
-        const float* p = x + ((long)d.y0 * W + d.x0) * ld_x + c;
-#define PP_DACC(ptr, wt)                                                                         \
-  if ((wt) != 0.f) { const float4 u = *reinterpret_cast<const float4*>(ptr);                    \
-    const float4 v = *reinterpret_cast<const float4*>((ptr) + 4);                               \
-    s0.x += u.x * (wt); s0.y += u.y * (wt); s0.z += u.z * (wt); s0.w += u.w * (wt);             \
-    s1.x += v.x * (wt); s1.y += v.y * (wt); s1.z += v.z * (wt); s1.w += v.w * (wt); }
-        PP_DACC(p, d.w00)
-        PP_DACC(p + ld_x, d.w01)
-        PP_DACC(p + (long)W * ld_x, d.w10)
-        PP_DACC(p + (long)W * ld_x + ld_x, d.w11)
-#undef PP_DACC
-      }
-      *reinterpret_cast<float4*>(&As[px_l][cseg * 8]) = s0;
-      *reinterpret_cast<float4*>(&As[px_l][cseg * 8 + 4]) = s1;
-      pp_cp_async_wait<0>();
-      __syncthreads();
+    for (int r = 0; r < 8; ++r) {
+      int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
+      pp_cp_async16(&Bs[buf][row][c4 * 4], Wp + ((long)it * 32 + row) * 128 + c4 * 4);   // rows of Wp are (k*Cin + c): it*32 == k*Cin + c0
+    }
+    pp_cp_async_commit();
+  };
+  auto store_a = [&](const DAGather& r, int buf) {
+    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8]) = r.s0;
+    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8 + 4]) = r.s1;
+  };
+
+  load_b(0, 0);
+  store_a(da_gather(x, ld_x, op, fp, max_res, H, W, cpg, 0, cseg * 8, y, xx, valid), 0);
+  pp_cp_async_wait<0>();
+  __syncthreads();
+
+  for (int it = 0; it < nit; ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const bool more = it + 1 < nit;
+    DAGather nx;
+    if (more) {
+      load_b(it + 1, nxt);
+      const int k1 = (it + 1) / cblocks, c1 = ((it + 1) - k1 * cblocks) * 32 + cseg * 8;
+      nx = da_gather(x, ld_x, op, fp, max_res, H, W, cpg, k1, c1, y, xx, valid);
+    }
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t a[4];
-        const int r0 = wm * 16 + g;
-        a[0] = pp_tf32(As[r0][ks * 8 + t]); a[1] = pp_tf32(As[r0 + 8][ks * 8 + t]);
-        a[2] = pp_tf32(As[r0][ks * 8 + t + 4]); a[3] = pp_tf32(As[r0 + 8][ks * 8 + t + 4]);
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      const int r0 = wm * 16 + g;
+      const float2 alo = *reinterpret_cast<const float2*>(&As[cur][r0][ks * 8 + 2 * t]);
+      const float2 ahi = *reinterpret_cast<const float2*>(&As[cur][r0 + 8][ks * 8 + 2 * t]);
+      a[0] = pp_tf32(alo.x); a[1] = pp_tf32(ahi.x); a[2] = pp_tf32(alo.y); a[3] = pp_tf32(ahi.y);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          uint32_t b[2];
-          const int n = wn * 64 + nt * 8 + g;
-          b[0] = pp_tf32(Bs[ks * 8 + t][n]); b[1] = pp_tf32(Bs[ks * 8 + t + 4][n]);
-          pp_mma_tf32(acc[nt], a, b);
-        }
+      for (int q = 0; q < 2; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][ks * 8 + 2 * t][wn * 64 + 32 * q + 4 * g]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][ks * 8 + 2 * t + 1][wn * 64 + 32 * q + 4 * g]);
+        uint32_t b[2];
+        b[0] = pp_tf32(b0.x); b[1] = pp_tf32(b1.x); pp_mma_tf32(acc[4 * q + 0], a, b);
+        b[0] = pp_tf32(b0.y); b[1] = pp_tf32(b1.y); pp_mma_tf32(acc[4 * q + 1], a, b);
+        b[0] = pp_tf32(b0.z); b[1] = pp_tf32(b1.z); pp_mma_tf32(acc[4 * q + 2], a, b);
+        b[0] = pp_tf32(b0.w); b[1] = pp_tf32(b1.w); pp_mma_tf32(acc[4 * q + 3], a, b);
       }
     }
+    if (more) {
+      store_a(nx, nxt);
+      pp_cp_async_wait<0>();
+    }
+    __syncthreads();
   }
+  // epilogue: tile 4q+j, C-fragment column 2t+c  <->  physical column wn*64 + 32q + 4(2t+c) + j
+  const long p0 = (long)blockIdx.x * 32 + wm * 16 + g, p1 = p0 + 8;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int n = wn * 64 + nt * 8 + 2 * t;
-    const float b0 = bias[n], b1 = bias[n + 1];
-    const long p0 = (long)blockIdx.x * 32 + wm * 16 + g, p1 = p0 + 8;
-    if (p0 < npix) { float2 v; v.x = acc[nt][0] + b0; v.y = acc[nt][1] + b1; *reinterpret_cast<float2*>(out + p0 * ld_out + n) = v; }
-    if (p1 < npix) { float2 v; v.x = acc[nt][2] + b0; v.y = acc[nt][3] + b1; *reinterpret_cast<float2*>(out + p1 * ld_out + n) = v; }
-  }
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int n = wn * 64 + 32 * q + 4 * (2 * t + c);
+      const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+      if (p0 < npix) {
+        float4 v = make_float4(acc[4 * q][c] + bv.x, acc[4 * q + 1][c] + bv.y, acc[4 * q + 2][c] + bv.z, acc[4 * q + 3][c] + bv.w);
+        *reinterpret_cast<float4*>(out + p0 * ld_out + n) = v;
+      }
+      if (p1 < npix) {
+        float4 v = make_float4(acc[4 * q][c + 2] + bv.x, acc[4 * q + 1][c + 2] + bv.y, acc[4 * q + 2][c + 2] + bv.z, acc[4 * q + 3][c + 2] + bv.w);
+        *reinterpret_cast<float4*>(out + p1 * ld_out + n) = v;
+      }
+    }
 }
 
 // replaces DeformableAlignment.forward / SecondOrderDeformableAlignment.forward after the offset-net
@@ -184,7 +229,7 @@ extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_
                                const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin,
                                int Cout, cudaStream_t stream) {
   if (Cout != 128 || Cin % 32 || (Cin / 16) % 8) return PP_ERR_SHAPE;
-  if (ld_x % 4 || ld_out % 2 || ld_o < 432) return PP_ERR_ALIGN;
+  if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
   const long npix = (long)H * W;
   k_deform_align<<<(int)((npix + 31) / 32), 128, 0, stream>>>(x, ld_x, o, ld_o, flow, max_res, w_packed, bias, out,
                                                              ld_out, H, W, Cin);
@@ -193,45 +238,85 @@ extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_
 }
 
 // ================================================================ sparse window attention
-// sparse_transformer.py:158-281.  One CTA = 64 query rows of one (window, head); flash-style online
+// sparse_transformer.py:158-281.  One CTA = NWARPS*16 query rows of one (window, head); flash-style online
 // softmax over key tiles of 64.  Keys of a masked window, per key frame: 45 own + 148 rolled (token
 // table) + pooled tokens; unmasked windows attend per frame to their own 45 tokens.  Nothing is
-// materialised: K/V rows (512 B per head) are gathered with cp.async straight from the QKV buffer.
-#define AT_LD 132
-template <bool MASKED>
-__global__ void __launch_bounds__(128) k_sparse_attn(PPAttnParams p) {
+// materialised: K/V rows (512 B per head) are gathered with cp.async straight from the QKV buffer into
+// a two-stage shared-memory ring, so the gather of tile i+1 overlaps the MMAs of tile i.
+// Fragment loads are 128-bit: for QK^T the 16 dims of two k-steps are renamed so a lane's float4 of K
+// (and of Q) covers (k=t, k=t+4) of both steps; for PV the 16 head-dim tiles are interleaved (physical
+// column 32q+4g+j <-> tile 4q+j, n=g) and P's C-fragment is reused as the A-fragment (keys 2t, 2t+1).
+#define AT_LDK 144
+#define AT_LDV 132
+#define AT_LDQ 136                       // query staging stride: 128 x 136 floats fit inside one stage
+#define AT_STAGE (64 * AT_LDK + 64 * AT_LDV)
+template <bool MASKED, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
   extern __shared__ __align__(16) float smem[];
-  float (*Ks)[AT_LD] = reinterpret_cast<float (*)[AT_LD]>(smem);
-  float (*Vs)[AT_LD] = reinterpret_cast<float (*)[AT_LD]>(smem + 64 * AT_LD);
+  constexpr int ROWS = NWARPS * 16, NT_ = NWARPS * 32;
   const int win = blockIdx.z, head = blockIdx.y;
   if (MASKED != (p.flags[win] != 0)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int* ktab = p.key_tok + (long)win * p.NKO;
   const int hoff = head * 128;
-  const int q0 = MASKED ? blockIdx.x * 64 : blockIdx.x * p.WN;
-  const int nq = MASKED ? min(64, p.t * p.WN - q0) : p.WN;
+  const int q0 = MASKED ? blockIdx.x * ROWS : blockIdx.x * p.WN;
+  const int nq = MASKED ? min(ROWS, p.t * p.WN - q0) : p.WN;
   const int keys_per_frame = p.NKO + p.NP;
   const int nkeys = MASKED ? p.nkf * keys_per_frame : p.WN;
+  const int ntiles = (nkeys + 63) / 64;
 
-  // ---- stage the query tile through Ks, pre-scaled into the log2 domain
-  for (int r = 0; r < 16; ++r) {
-    int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
+  auto Kst = [&](int st) { return smem + st * AT_STAGE; };
+  auto Vst = [&](int st) { return smem + st * AT_STAGE + 64 * AT_LDK; };
+  auto gather = [&](int tile, int st) {
+    float* Ks = Kst(st); float* Vs = Vst(st);
+    for (int idx = tid; idx < 64 * 32; idx += NT_) {
+      const int key = idx >> 5, c4 = idx & 31, j = tile * 64 + key;
+      if (j < nkeys) {
+        const float* src;
+        if (MASKED) {
+          const int kfi = j / keys_per_frame, slot = j - kfi * keys_per_frame;
+          const int fr = p.kf_start + kfi * p.kf_step;
+          if (slot < p.NKO) src = p.qkv + ((long)fr * p.NT + ktab[slot]) * p.ld_qkv + p.C + hoff;
+          else src = p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + hoff;          // pool rows: K at 0, V at C
+        } else {
+          src = p.qkv + ((long)blockIdx.x * p.NT + ktab[j]) * p.ld_qkv + p.C + hoff;
+        }
+        pp_cp_async16(Ks + key * AT_LDK + c4 * 4, src + c4 * 4);
+        pp_cp_async16(Vs + key * AT_LDV + c4 * 4, src + p.C + c4 * 4);
+      } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(Ks + key * AT_LDK + c4 * 4) = z;
+        *reinterpret_cast<float4*>(Vs + key * AT_LDV + c4 * 4) = z;
+      }
+    }
+    pp_cp_async_commit();
+  };
+
+  // ---- stage the query tile through stage 1 (free until the second key tile), scaled into the log2 domain
+  static_assert(ROWS * AT_LDQ <= AT_STAGE, "query tile must fit in one stage");
+  float* Qs = Kst(1);
+  for (int idx = tid; idx < ROWS * 32; idx += NT_) {
+    const int row = idx >> 5, c4 = idx & 31;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < nq) {
-      int qi = q0 + row, fr = qi / p.WN, tok = ktab[qi - fr * p.WN];
+      const int qi = q0 + row, fr = qi / p.WN, tok = ktab[qi - fr * p.WN];
       v = *reinterpret_cast<const float4*>(p.qkv + ((long)fr * p.NT + tok) * p.ld_qkv + hoff + c4 * 4);
     }
     v.x *= p.scale_log2; v.y *= p.scale_log2; v.z *= p.scale_log2; v.w *= p.scale_log2;
-    *reinterpret_cast<float4*>(&Ks[row][c4 * 4]) = v;
+    *reinterpret_cast<float4*>(Qs + row * AT_LDQ + c4 * 4) = v;
   }
+  gather(0, 0);
   __syncthreads();
   uint32_t qa[16][4];
   {
-    const int r0 = warp * 16 + g;
+    const float* r0 = Qs + (warp * 16 + g) * AT_LDQ;
+    const float* r1 = r0 + 8 * AT_LDQ;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {
-      qa[ks][0] = pp_tf32(Ks[r0][ks * 8 + t]); qa[ks][1] = pp_tf32(Ks[r0 + 8][ks * 8 + t]);
-      qa[ks][2] = pp_tf32(Ks[r0][ks * 8 + t + 4]); qa[ks][3] = pp_tf32(Ks[r0 + 8][ks * 8 + t + 4]);
+    for (int j = 0; j < 8; ++j) {                                         // dims 16j .. 16j+15 = k-steps 2j, 2j+1
+      const float4 lo = *reinterpret_cast<const float4*>(r0 + 16 * j + 4 * t);
+      const float4 hi = *reinterpret_cast<const float4*>(r1 + 16 * j + 4 * t);
+      qa[2 * j][0] = pp_tf32(lo.x); qa[2 * j][1] = pp_tf32(hi.x); qa[2 * j][2] = pp_tf32(lo.y); qa[2 * j][3] = pp_tf32(hi.y);
+      qa[2 * j + 1][0] = pp_tf32(lo.z); qa[2 * j + 1][1] = pp_tf32(hi.z); qa[2 * j + 1][2] = pp_tf32(lo.w); qa[2 * j + 1][3] = pp_tf32(hi.w);
     }
   }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -241,50 +326,32 @@ __global__ void __launch_bounds__(128) k_sparse_attn(PPAttnParams p) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) oacc[a][b] = 0.f;
 
-  for (int kt0 = 0; kt0 < nkeys; kt0 += 64) {
-    __syncthreads();
-    // ---- gather 64 keys x 128 dims of K and V
-    for (int r = 0; r < 16; ++r) {
-      int idx = tid + 128 * r, key = idx >> 5, c4 = idx & 31;
-      int j = kt0 + key;
-      if (j < nkeys) {
-        const float* src;
-        if (MASKED) {
-          int kfi = j / keys_per_frame, slot = j - kfi * keys_per_frame;
-          int fr = p.kf_start + kfi * p.kf_step;
-          if (slot < p.NKO) src = p.qkv + ((long)fr * p.NT + ktab[slot]) * p.ld_qkv + p.C + hoff;
-          else src = p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + hoff;          // pool rows: K at 0, V at C
-        } else {
-          src = p.qkv + ((long)blockIdx.x * p.NT + ktab[j]) * p.ld_qkv + p.C + hoff;
-        }
-        pp_cp_async16(&Ks[key][c4 * 4], src + c4 * 4);
-        pp_cp_async16(&Vs[key][c4 * 4], src + p.C + c4 * 4);
-      } else {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(&Ks[key][c4 * 4]) = z;
-        *reinterpret_cast<float4*>(&Vs[key][c4 * 4]) = z;
-      }
-    }
-    pp_cp_async_commit();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int cur = tile & 1;
     pp_cp_async_wait<0>();
-    __syncthreads();
+    __syncthreads();                          // tile landed; every warp is done with the other stage (and with Qs)
+    if (tile + 1 < ntiles) gather(tile + 1, cur ^ 1);
+    const float* Ks = Kst(cur); const float* Vs = Vst(cur);
+    const int kt0 = tile * 64;
 
     // ---- S = Q K^T (already scaled, log2 domain)
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const float* kr = Ks + (nt * 8 + g) * AT_LDK + 4 * t;
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 kv = *reinterpret_cast<const float4*>(kr + 16 * j);
         uint32_t b[2];
-        b[0] = pp_tf32(Ks[nt * 8 + g][ks * 8 + t]); b[1] = pp_tf32(Ks[nt * 8 + g][ks * 8 + t + 4]);
-        pp_mma_tf32(s[nt], qa[ks], b);
+        b[0] = pp_tf32(kv.x); b[1] = pp_tf32(kv.y); pp_mma_tf32(s[nt], qa[2 * j], b);
+        b[0] = pp_tf32(kv.z); b[1] = pp_tf32(kv.w); pp_mma_tf32(s[nt], qa[2 * j + 1], b);
       }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      int j = kt0 + nt * 8 + 2 * t;
+      const int j = kt0 + nt * 8 + 2 * t;
       if (j >= nkeys) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
       if (j + 1 >= nkeys) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
@@ -306,16 +373,20 @@ __global__ void __launch_bounds__(128) k_sparse_attn(PPAttnParams p) {
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) { oacc[nt][0] *= al0; oacc[nt][1] *= al0; oacc[nt][2] *= al1; oacc[nt][3] *= al1; }
 
-    // ---- O += P V.  P's C-fragment is reused as the A-fragment by renaming the k index inside each
-    // 8-key group (k=t <-> key 2t, k=t+4 <-> key 2t+1); V rows are fetched with the same renaming.
+    // ---- O += P V
 #pragma unroll
     for (int kg = 0; kg < 8; ++kg) {
-      uint32_t a[4] = {pp_tf32(s[kg][0]), pp_tf32(s[kg][2]), pp_tf32(s[kg][1]), pp_tf32(s[kg][3])};
+      const uint32_t a[4] = {pp_tf32(s[kg][0]), pp_tf32(s[kg][2]), pp_tf32(s[kg][1]), pp_tf32(s[kg][3])};
+      const float* v0 = Vs + (kg * 8 + 2 * t) * AT_LDV + 4 * g;
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
+      for (int q = 0; q < 4; ++q) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v0 + 32 * q);
+        const float4 x1 = *reinterpret_cast<const float4*>(v0 + AT_LDV + 32 * q);
         uint32_t b[2];
-        b[0] = pp_tf32(Vs[kg * 8 + 2 * t][nt * 8 + g]); b[1] = pp_tf32(Vs[kg * 8 + 2 * t + 1][nt * 8 + g]);
-        pp_mma_tf32(oacc[nt], a, b);
+        b[0] = pp_tf32(x0.x); b[1] = pp_tf32(x1.x); pp_mma_tf32(oacc[4 * q + 0], a, b);
+        b[0] = pp_tf32(x0.y); b[1] = pp_tf32(x1.y); pp_mma_tf32(oacc[4 * q + 1], a, b);
+        b[0] = pp_tf32(x0.z); b[1] = pp_tf32(x1.z); pp_mma_tf32(oacc[4 * q + 2], a, b);
+        b[0] = pp_tf32(x0.w); b[1] = pp_tf32(x1.w); pp_mma_tf32(oacc[4 * q + 3], a, b);
       }
     }
   }
@@ -326,26 +397,31 @@ __global__ void __launch_bounds__(128) k_sparse_attn(PPAttnParams p) {
   float* oa = nullptr; float* ob = nullptr;
   if (ra < nq) { int qi = q0 + ra, fr = qi / p.WN; oa = p.out + ((long)fr * p.NT + ktab[qi - fr * p.WN]) * p.ld_out + hoff; }
   if (rb < nq) { int qi = q0 + rb, fr = qi / p.WN; ob = p.out + ((long)fr * p.NT + ktab[qi - fr * p.WN]) * p.ld_out + hoff; }
+  // tile 4q+j, C-fragment column 2t+c  <->  head-dim column 32q + 4(2t+c) + j
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) {
-    if (oa) { float2 v; v.x = oacc[nt][0] * inv0; v.y = oacc[nt][1] * inv0; *reinterpret_cast<float2*>(oa + nt * 8 + 2 * t) = v; }
-    if (ob) { float2 v; v.x = oacc[nt][2] * inv1; v.y = oacc[nt][3] * inv1; *reinterpret_cast<float2*>(ob + nt * 8 + 2 * t) = v; }
-  }
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int n = 32 * q + 4 * (2 * t + c);
+      if (oa) *reinterpret_cast<float4*>(oa + n) = make_float4(oacc[4 * q][c] * inv0, oacc[4 * q + 1][c] * inv0, oacc[4 * q + 2][c] * inv0, oacc[4 * q + 3][c] * inv0);
+      if (ob) *reinterpret_cast<float4*>(ob + n) = make_float4(oacc[4 * q][c + 2] * inv1, oacc[4 * q + 1][c + 2] * inv1, oacc[4 * q + 2][c + 2] * inv1, oacc[4 * q + 3][c + 2] * inv1);
+    }
 }
 
 // replaces SparseWindowAttention.forward between the q/k/v Linear layers and `proj`
 // (model/modules/sparse_transformer.py:177-275)
 extern "C" int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream) {
   const PPAttnParams& p = *prm;
-  if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 2) return PP_ERR_SHAPE;
-  const int smem = 2 * 64 * AT_LD * (int)sizeof(float);
-  if (cudaFuncSetAttribute(k_sparse_attn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sparse_attn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 4) return PP_ERR_SHAPE;
+  if (((uintptr_t)p.qkv & 15) || ((uintptr_t)p.pool & 15) || ((uintptr_t)p.out & 15)) return PP_ERR_ALIGN;
+  const int smem = 2 * AT_STAGE * (int)sizeof(float);
+  if (cudaFuncSetAttribute(k_sparse_attn<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_sparse_attn<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return PP_ERR_LAUNCH;
   const int heads = p.C / 128;
-  dim3 gm((p.t * p.WN + 63) / 64, heads, n_windows), gu(p.t, heads, n_windows);
-  k_sparse_attn<true><<<gm, 128, smem, stream>>>(p);
-  k_sparse_attn<false><<<gu, 128, smem, stream>>>(p);
+  dim3 gm((p.t * p.WN + 127) / 128, heads, n_windows), gu(p.t, heads, n_windows);
+  k_sparse_attn<true, 8><<<gm, 256, smem, stream>>>(p);
+  k_sparse_attn<false, 4><<<gu, 128, smem, stream>>>(p);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

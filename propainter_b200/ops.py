@@ -199,6 +199,36 @@ def ffn_overlap_add(Y, frames, h, w, CH=40):
     return Z
 
 
+def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
+    """zr_pm [..,2C] raw gate conv output; net_view / rnet_view: C-channel slices of HX / RX; z_out dense [..,C]."""
+    C = z_out.shape[-1]
+    np_, ldn = _pm(net_view)
+    rp, ldr = _pm(rnet_view)
+    check(_lib.lib().pp_gru_gate(_p(_dense(zr_pm)), _p(bias), np_, ldn, _p(_dense(z_out)), rp, ldr, z_out.numel() // C, C,
+                                 _stream()), "pp_gru_gate")
+    _count(1)
+
+
+def gru_update(q_pm, bias, z, net_view):
+    C = z.shape[-1]
+    np_, ldn = _pm(net_view)
+    check(_lib.lib().pp_gru_update(_p(_dense(q_pm)), _p(bias), _p(_dense(z)), np_, ldn, z.numel() // C, C, _stream()),
+          "pp_gru_update")
+    _count(1)
+
+
+def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view):
+    """mot_pm [..,128] (channels 126,127 ignored), flow_pm [..,2] -> 128-channel slot views of HX and RX."""
+    mp, ldm = _pm(mot_pm)
+    p0, ld0 = _pm(d0_view)
+    p1, ld1 = _pm(d1_view)
+    if ld0 != ld1:
+        raise RuntimeError("HX / RX must share the pixel stride")
+    check(_lib.lib().pp_raft_pack_motion(mp, ldm, _p(_dense(flow_pm)), p0, p1, ld0, flow_pm.numel() // 2, _stream()),
+          "pp_raft_pack_motion")
+    _count(1)
+
+
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
 
 

@@ -141,6 +141,20 @@ def install(monkeypatch, hostsim):
          "sigmoid": lambda: torch.sigmoid_(x_pm), "tanh": lambda: torch.tanh_(x_pm)}[act]()
         return x_pm
 
+    def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
+        C = z_out.shape[-1]
+        g = torch.sigmoid(zr_pm + bias)
+        z_out.copy_(g[..., :C])
+        rnet_view.copy_(g[..., C:] * net_view)
+
+    def gru_update(q_pm, bias, z, net_view):
+        net_view.copy_((1 - z) * net_view + z * torch.tanh(q_pm + bias))
+
+    def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view):
+        v = torch.cat([mot_pm[..., :126], flow_pm], -1)
+        d0_view.copy_(v)
+        d1_view.copy_(v)
+
     def upsample2x(x_pm):
         n, h, w, C = x_pm.shape
         x_pm = x_pm.contiguous()

@@ -248,6 +248,30 @@ def test_bias_act_and_upsample2x():
         assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
 
 
+def test_gru_fusion_kernels():
+    """SepConvGRU elementwise rules (RAFT/update.py:45-60) on slices of the persistent HX / RX buffers."""
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    B, h, w, C = 2, 9, 13, 128
+    HX, RX = torch.randn(B, h, w, 384, generator=gen), torch.randn(B, h, w, 384, generator=gen)
+    zr, q = torch.randn(B, h, w, 2 * C, generator=gen) * 2, torch.randn(B, h, w, C, generator=gen) * 2
+    bzr, bq = torch.randn(2 * C, generator=gen), torch.randn(C, generator=gen)
+    mot, flow = torch.randn(B, h, w, 128, generator=gen), torch.randn(B, h, w, 2, generator=gen)
+    hx, rx = HX.to(DEV), RX.to(DEV)
+    z = torch.empty(B, h, w, C, device=DEV)
+    ops.gru_gate(zr.to(DEV), bzr.to(DEV), hx[..., :C], z, rx[..., :C])
+    g = torch.sigmoid(zr + bzr)
+    assert torch.allclose(z.cpu(), g[..., :C], atol=2e-6) and torch.allclose(rx.cpu()[..., :C], g[..., C:] * HX[..., :C], atol=5e-6)
+    assert torch.equal(rx.cpu()[..., C:], RX[..., C:]) and torch.equal(hx.cpu(), HX)
+    ops.gru_update(q.to(DEV), bq.to(DEV), z, hx[..., :C])
+    ref = (1 - g[..., :C]) * HX[..., :C] + g[..., :C] * torch.tanh(q + bq)
+    assert torch.allclose(hx.cpu()[..., :C], ref, atol=5e-6) and torch.equal(hx.cpu()[..., C:], HX[..., C:])
+    ops.raft_pack_motion(mot.to(DEV), flow.to(DEV), hx[..., 256:], rx[..., 256:])
+    want = torch.cat([mot[..., :126], flow], -1)
+    assert torch.equal(hx.cpu()[..., 256:], want) and torch.equal(rx.cpu()[..., 256:], want)
+    assert torch.equal(hx.cpu()[..., C:256], HX[..., C:256])
+
+
 def test_u8_and_composite():
     from oracle import pipeline_ref
     from propainter_b200 import ops
