@@ -63,9 +63,10 @@ int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int ld_prop, c
  * model/recurrent_flow_completion.py:31-44 after the conv_offset stack (torchvision.ops.deform_conv2d,
  * 3x3/s1/p1, 16 deform groups).  x pixel-major [H*W][ld_x] (Cin), o = raw conv_offset output
  * [H*W][ld_o>=432], flow [H*W][2] or NULL, w_packed [9*Cin][128] (row = tap*Cin + c), out [H*W][ld_out]. */
+size_t pp_deform_align_workspace_bytes(int H, int W);   /* split-K partial sums for small maps; may be 0 */
 int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
                     const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin, int Cout,
-                    cudaStream_t stream);
+                    void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* ---- generator glue ------------------------------------------------------------------------- */
 /* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar
@@ -90,6 +91,8 @@ typedef struct PPAttnParams {
 } PPAttnParams;
 /* SparseWindowAttention.forward model/modules/sparse_transformer.py:177-275 (between q/k/v and proj). */
 int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream);
+/* same contract; masked windows on the warp-level mma.sync kernel (baseline of the tcgen05/TMEM kernel) */
+int pp_sparse_window_attn_mma(const PPAttnParams* prm, int n_windows, cudaStream_t stream);
 
 /* FusionFeedForward.forward model/modules/sparse_transformer.py:81-100: fold -> /normalizer -> unfold -> GELU.
  * Y,Z [frames*fh*fw][ld], hidden columns tap-major (tap*CH + c). */

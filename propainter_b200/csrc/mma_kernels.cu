@@ -134,7 +134,9 @@ __device__ __forceinline__ DAGather da_gather(const float* __restrict__ x, int l
 
 __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float* __restrict__ o,
     int ld_o, const float* __restrict__ flow, float max_res, const float* __restrict__ Wp,
-    const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin) {
+    const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin, float* __restrict__ part) {
+  // gridDim.y > 1: split-K over the 9*Cin/32 K-steps -- CTA row y accumulates its share into part[y][pix][128]
+  // (reduced + biased by k_deform_reduce); a 6480- or 1620-pixel map alone gives only 203 / 51 CTAs.
   __shared__ __align__(16) float As[2][32][DA_LDA];
   __shared__ __align__(16) float Bs[2][32][DA_LDB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
   const long pix = (long)blockIdx.x * 32 + px_l;
   const bool valid = pix < npix;
   const int y = valid ? (int)(pix / W) : 0, xx = valid ? (int)(pix - (long)y * W) : 0;
-  const int cpg = Cin / 16, cblocks = Cin / 32, nit = 9 * cblocks;
+  const int cpg = Cin / 16, cblocks = Cin / 32, nit_all = 9 * cblocks;
+  const int it0 = (int)((long)nit_all * blockIdx.y / gridDim.y), it1 = (int)((long)nit_all * (blockIdx.y + 1) / gridDim.y);
   const float* op = o + (valid ? pix : 0) * ld_o;
   const float* fp = flow ? flow + 2 * (valid ? pix : 0) : nullptr;
   float acc[8][4];
@@ -166,14 +169,17 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
     *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8 + 4]) = r.s1;
   };
 
-  load_b(0, 0);
-  store_a(da_gather(x, ld_x, op, fp, max_res, H, W, cpg, 0, cseg * 8, y, xx, valid), 0);
+  load_b(it0, 0);
+  {
+    const int k0 = it0 / cblocks;
+    store_a(da_gather(x, ld_x, op, fp, max_res, H, W, cpg, k0, (it0 - k0 * cblocks) * 32 + cseg * 8, y, xx, valid), 0);
+  }
   pp_cp_async_wait<0>();
   __syncthreads();
 
-  for (int it = 0; it < nit; ++it) {
-    const int cur = it & 1, nxt = cur ^ 1;
-    const bool more = it + 1 < nit;
+  for (int it = it0; it < it1; ++it) {
+    const int cur = (it - it0) & 1, nxt = cur ^ 1;
+    const bool more = it + 1 < it1;
     DAGather nx;
     if (more) {
       load_b(it + 1, nxt);
@@ -206,33 +212,66 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
   }
   // epilogue: tile 4q+j, C-fragment column 2t+c  <->  physical column wn*64 + 32q + 4(2t+c) + j
   const long p0 = (long)blockIdx.x * 32 + wm * 16 + g, p1 = p0 + 8;
+  const bool split = gridDim.y > 1;
+  float* dst = split ? part + (long)blockIdx.y * npix * 128 : out;
+  const int ldd = split ? 128 : ld_out;
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int n = wn * 64 + 32 * q + 4 * (2 * t + c);
-      const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!split) bv = *reinterpret_cast<const float4*>(bias + n);
       if (p0 < npix) {
         float4 v = make_float4(acc[4 * q][c] + bv.x, acc[4 * q + 1][c] + bv.y, acc[4 * q + 2][c] + bv.z, acc[4 * q + 3][c] + bv.w);
-        *reinterpret_cast<float4*>(out + p0 * ld_out + n) = v;
+        *reinterpret_cast<float4*>(dst + p0 * ldd + n) = v;
       }
       if (p1 < npix) {
         float4 v = make_float4(acc[4 * q][c + 2] + bv.x, acc[4 * q + 1][c + 2] + bv.y, acc[4 * q + 2][c + 2] + bv.z, acc[4 * q + 3][c + 2] + bv.w);
-        *reinterpret_cast<float4*>(out + p1 * ld_out + n) = v;
+        *reinterpret_cast<float4*>(dst + p1 * ldd + n) = v;
       }
     }
+}
+
+__global__ void __launch_bounds__(256) k_deform_reduce(const float* __restrict__ part, const float* __restrict__ bias,
+                                                       float* __restrict__ out, int ld_out, long npix, int splits) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // over npix*32 float4
+  if (i >= npix * 32) return;
+  const long pix = i >> 5; const int n = (int)(i & 31) * 4;
+  float4 s = *reinterpret_cast<const float4*>(bias + n);
+  for (int k = 0; k < splits; ++k) {                                // fixed order: deterministic
+    const float4 v = *reinterpret_cast<const float4*>(part + ((long)k * npix + pix) * 128 + n);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + pix * ld_out + n) = s;
+}
+
+static int da_splits(long npix) {
+  const long ctas = (npix + 31) / 32;
+  if (ctas >= 4 * PP_NUM_SMS) return 1;
+  return ctas * 3 >= 3 * PP_NUM_SMS ? 3 : 9;
+}
+extern "C" size_t pp_deform_align_workspace_bytes(int H, int W) {
+  const long npix = (long)H * W;
+  const int s = da_splits(npix);
+  return s > 1 ? (size_t)s * npix * 128 * sizeof(float) : 0;
 }
 
 // replaces DeformableAlignment.forward / SecondOrderDeformableAlignment.forward after the offset-net
 // convs (model/propainter.py:57-69, model/recurrent_flow_completion.py:31-44 -> torchvision deform_conv2d)
 extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
                                const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin,
-                               int Cout, cudaStream_t stream) {
+                               int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   if (Cout != 128 || Cin % 32 || (Cin / 16) % 8) return PP_ERR_SHAPE;
   if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
   const long npix = (long)H * W;
-  k_deform_align<<<(int)((npix + 31) / 32), 128, 0, stream>>>(x, ld_x, o, ld_o, flow, max_res, w_packed, bias, out,
-                                                             ld_out, H, W, Cin);
+  const int splits = da_splits(npix);
+  if (ws_bytes < pp_deform_align_workspace_bytes(H, W) || (splits > 1 && ((uintptr_t)workspace & 15))) return PP_ERR_WORKSPACE;
+  dim3 grid((unsigned)((npix + 31) / 32), splits);
+  k_deform_align<<<grid, 128, 0, stream>>>(x, ld_x, o, ld_o, flow, max_res, w_packed, bias, out, ld_out, H, W, Cin,
+                                           (float*)workspace);
+  if (splits > 1)
+    k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>((const float*)workspace, bias, out, ld_out, npix, splits);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -294,7 +333,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
 
   // ---- stage the query tile through stage 1 (free until the second key tile), scaled into the log2 domain
   static_assert(ROWS * AT_LDQ <= AT_STAGE, "query tile must fit in one stage");
-  float* Qs = Kst(1);
+  // masked: Q is staged through stage 1 (free until the 2nd key tile); unmasked windows have a single key tile and
+  // run with ONE stage of shared memory (3 CTAs/SM instead of 1): Q goes through stage 0 before the gather.
+  float* Qs = MASKED ? Kst(1) : Kst(0);
   for (int idx = tid; idx < ROWS * 32; idx += NT_) {
     const int row = idx >> 5, c4 = idx & 31;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -305,7 +346,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
     v.x *= p.scale_log2; v.y *= p.scale_log2; v.z *= p.scale_log2; v.w *= p.scale_log2;
     *reinterpret_cast<float4*>(Qs + row * AT_LDQ + c4 * 4) = v;
   }
-  gather(0, 0);
+  if (MASKED) gather(0, 0);
   __syncthreads();
   uint32_t qa[16][4];
   {
@@ -319,6 +360,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
       qa[2 * j + 1][0] = pp_tf32(lo.z); qa[2 * j + 1][1] = pp_tf32(hi.z); qa[2 * j + 1][2] = pp_tf32(lo.w); qa[2 * j + 1][3] = pp_tf32(hi.w);
     }
   }
+  if (!MASKED) { __syncthreads(); gather(0, 0); }          // every warp has its Q fragments; stage 0 may be overwritten
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float oacc[16][4];
 #pragma unroll
@@ -408,20 +450,45 @@ __global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
     }
 }
 
-// replaces SparseWindowAttention.forward between the q/k/v Linear layers and `proj`
-// (model/modules/sparse_transformer.py:177-275)
-extern "C" int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream) {
-  const PPAttnParams& p = *prm;
+int pp_launch_sparse_attn_umma(const PPAttnParams& p, int n_windows, cudaStream_t stream);   // attn_umma.cu
+
+static int pp_attn_check(const PPAttnParams& p) {
   if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 4) return PP_ERR_SHAPE;
   if (((uintptr_t)p.qkv & 15) || ((uintptr_t)p.pool & 15) || ((uintptr_t)p.out & 15)) return PP_ERR_ALIGN;
-  const int smem = 2 * AT_STAGE * (int)sizeof(float);
-  if (cudaFuncSetAttribute(k_sparse_attn<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-      cudaFuncSetAttribute(k_sparse_attn<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  return PP_OK;
+}
+static int pp_attn_unmasked(const PPAttnParams& p, int n_windows, cudaStream_t stream) {
+  const int smem1 = AT_STAGE * (int)sizeof(float);
+  if (cudaFuncSetAttribute(k_sparse_attn<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1) != cudaSuccess)
     return PP_ERR_LAUNCH;
-  const int heads = p.C / 128;
-  dim3 gm((p.t * p.WN + 127) / 128, heads, n_windows), gu(p.t, heads, n_windows);
-  k_sparse_attn<true, 8><<<gm, 256, smem, stream>>>(p);
-  k_sparse_attn<false, 4><<<gu, 128, smem, stream>>>(p);
+  dim3 gu(p.t, p.C / 128, n_windows);
+  k_sparse_attn<false, 4><<<gu, 128, smem1, stream>>>(p);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+// replaces SparseWindowAttention.forward between the q/k/v Linear layers and `proj`
+// (model/modules/sparse_transformer.py:177-275).  Masked windows: tcgen05/TMEM kernel (attn_umma.cu);
+// unmasked windows (45x45 per frame): warp-level mma.sync kernel above.
+extern "C" int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cudaStream_t stream) {
+  const PPAttnParams& p = *prm;
+  int rc = pp_attn_check(p);
+  if (rc != PP_OK) return rc;
+  rc = pp_launch_sparse_attn_umma(p, n_windows, stream);
+  if (rc != PP_OK) return rc;
+  return pp_attn_unmasked(p, n_windows, stream);
+}
+
+// same contract, masked windows on the warp-level mma.sync kernel (measured baseline of the tcgen05 kernel)
+extern "C" int pp_sparse_window_attn_mma(const PPAttnParams* prm, int n_windows, cudaStream_t stream) {
+  const PPAttnParams& p = *prm;
+  int rc = pp_attn_check(p);
+  if (rc != PP_OK) return rc;
+  const int smem = 2 * AT_STAGE * (int)sizeof(float);
+  if (cudaFuncSetAttribute(k_sparse_attn<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return PP_ERR_LAUNCH;
+  dim3 gm((p.t * p.WN + 127) / 128, p.C / 128, n_windows);
+  k_sparse_attn<true, 8><<<gm, 256, smem, stream>>>(p);
+  PP_LAUNCH_CHECK();
+  return pp_attn_unmasked(p, n_windows, stream);
 }

@@ -133,9 +133,12 @@ def deform_align(x, o, flow, max_res, w_packed, bias, out):
     xp, ldx = _pm(x)
     op, ldo = _pm(o)
     outp, ldout = _pm(out)
-    check(_lib.lib().pp_deform_align(xp, ldx, op, ldo, _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp,
-                                     ldout, H, W, Cin, out.shape[-1], _stream()), "pp_deform_align")
-    _count(1)
+    L = _lib.lib()
+    ws_bytes = L.pp_deform_align_workspace_bytes(H, W)
+    ws = torch.empty(max(ws_bytes // 4, 4), device=x.device, dtype=torch.float32)
+    check(L.pp_deform_align(xp, ldx, op, ldo, _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp, ldout, H, W,
+                            Cin, out.shape[-1], _p(ws), ws_bytes, _stream()), "pp_deform_align")
+    _count(2 if ws_bytes else 1)
     return out
 
 
@@ -168,8 +171,9 @@ def window_mask(pmask, fh, fw, nwh, nww):
     return flags
 
 
-def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, out=None, WN=45, C=512):
-    """qkv [t,NT,3C]; pool_kv [t,NP,2C]; key_tok int32 [nwin,NKO]; flags int32 [nwin] -> out [t,NT,C]."""
+def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, out=None, WN=45, C=512, impl="umma"):
+    """qkv [t,NT,3C]; pool_kv [t,NP,2C]; key_tok int32 [nwin,NKO]; flags int32 [nwin] -> out [t,NT,C].
+    impl: "umma" = tcgen05/TMEM kernel for masked windows (default), "mma" = warp-level mma.sync baseline."""
     if out is None:
         out = torch.empty(t, NT, C, device=qkv.device, dtype=torch.float32)
     prm = PPAttnParams()
@@ -182,7 +186,8 @@ def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, o
     prm.scale_log2 = LOG2E / math.sqrt(128.0)
     for tns, dt in ((qkv, torch.float32), (pool_kv, torch.float32), (key_tok, torch.int32), (flags, torch.int32)):
         _p(_dense(tns), dt)
-    check(_lib.lib().pp_sparse_window_attn(ctypes.byref(prm), key_tok.shape[0], _stream()), "pp_sparse_window_attn")
+    fn = _lib.lib().pp_sparse_window_attn if impl == "umma" else _lib.lib().pp_sparse_window_attn_mma
+    check(fn(ctypes.byref(prm), key_tok.shape[0], _stream()), "pp_sparse_window_attn")
     _count(2)
     return out
 

@@ -209,10 +209,12 @@ def test_sparse_window_attention():
             mp = F.pad(mask[0, ..., 0], (0, W2 - fw, 0, H2 - fh))
             flags = (F.max_pool2d(mp[:, None], (5, 9), (5, 9)).view(lt, -1).sum(0) > 0).int().to(DEV)
             ktab = torch.from_numpy(window_key_table(H2, W2)).to(DEV)
-            got = ops.sparse_window_attn(qkv, pool_kv, ktab, flags, t, H2 * W2, layer % 2, 2).view(t, H2, W2, C)[:, :fh, :fw].cpu()
-            scale = ref.abs().max().item()
-            err = (got - ref).abs().max().item()
-            assert err < 3e-3 * scale, (t, fh, fw, layer, err, scale)
+            for impl in ("umma", "mma"):
+                got = ops.sparse_window_attn(qkv, pool_kv, ktab, flags, t, H2 * W2, layer % 2, 2, impl=impl)
+                got = got.view(t, H2, W2, C)[:, :fh, :fw].cpu()
+                scale = ref.abs().max().item()
+                err = (got - ref).abs().max().item()
+                assert err < 3e-3 * scale, (impl, t, fh, fw, layer, err, scale)
 
 
 def test_ffn_overlap_add():
