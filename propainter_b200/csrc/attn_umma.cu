@@ -12,7 +12,8 @@
 //               warps transpose V while staging it; bank-conflict free), D = O in TMEM (128 columns)
 // O is rescaled in TMEM only when a row maximum grows by more than 2^8 (lazy rescaling); the final 1/l is
 // applied in the epilogue.  Roles: warps 0-3 softmax / correction / epilogue (one query row per thread =
-// one TMEM lane), warps 4-7 K/V producers (cp.async + transposing stores), warp 8 TMEM allocator + MMA issuer.
+// one TMEM lane), warps 4-11 K/V producers (cp.async + transposing stores; two groups on alternate tiles), warp 12 TMEM
+// allocator + MMA issuer.  Q lives in TMEM too (A operand of S), which leaves shared memory for a 3-stage K/V ring.
 // All waits are bounded and trap instead of hanging.  Descriptor encodings were validated in isolation
 // with profiles/probes/umma_probe.cu (variants 0 and 3).
 #include "pp_elem.cuh"
@@ -21,12 +22,15 @@
 
 #define UA_BM 128
 #define UA_BN 64
-#define UA_THREADS 288
-#define UA_Q_BYTES (UA_BM * 128 * 4)               // 64 KB: 4 k-blocks of [128 rows x 128 B]
+#define UA_THREADS 416                             // 4 softmax + 8 producer (two groups on alternate tiles) + 1 MMA warp
 #define UA_K_BYTES (UA_BN * 128 * 4)               // 32 KB: 4 k-blocks of [64 rows x 128 B]
 #define UA_V_BYTES (128 * UA_BN * 4)               // 32 KB: 2 k-blocks of [128 rows x 128 B]  (V^T: rows = head dim)
 #define UA_STAGE_BYTES (UA_K_BYTES + UA_V_BYTES)
-#define UA_SMEM_BYTES (UA_Q_BYTES + 2 * UA_STAGE_BYTES + 1024)
+#define UA_STAGES 2                                // one K/V stage per producer group
+#define UA_LDSTG 132                               // V staging rows: 128 floats + 4 pad (conflict-free LDS.128 by key)
+#define UA_STG_BYTES (UA_BN * UA_LDSTG * 4)
+#define UA_TAIL_BYTES 3072                          // barriers, TMEM base (+128), token table (<= 224 ints at +256), key row pointers (+1152)
+#define UA_SMEM_BYTES (UA_STAGES * (UA_STAGE_BYTES + UA_STG_BYTES) + UA_TAIL_BYTES + 1024)
 
 __device__ __forceinline__ uint32_t ua_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ua_bar_init(uint32_t bar, int count) {
@@ -34,6 +38,17 @@ __device__ __forceinline__ void ua_bar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void ua_bar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool ua_bar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ float ua_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void ua_bar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -79,13 +94,16 @@ __device__ __forceinline__ void ua_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
 
 __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams p) {
   extern __shared__ __align__(1024) uint8_t ua_raw[];
-  // barriers: 0,1 kv_full[2]  2,3 kv_empty[2]  4,5 s_full[2]  6,7 p_full[2]  8 pv_done
-  __shared__ __align__(8) unsigned long long bars[9];
-  __shared__ uint32_t tmem_base_s;
   const int win = blockIdx.z, head = blockIdx.y;
   if (p.flags[win] == 0) return;
-  uint8_t* base = (uint8_t*)(((uintptr_t)ua_raw + 1023) & ~(uintptr_t)1023);        // SWIZZLE_128B tiles need 1 KB alignment
-  uint8_t* sQ = base;
+  // SWIZZLE_128B tiles need 1 KB alignment; the pad is applied as an offset so the pointer stays in the shared window
+  uint8_t* base = ua_raw + ((1024u - (ua_smem(ua_raw) & 1023u)) & 1023u);
+  uint8_t* stg_base = base + UA_STAGES * UA_STAGE_BYTES;             // per-group V staging (row-major, padded)
+  uint8_t* tail = stg_base + UA_STAGES * UA_STG_BYTES;
+  // barriers: 0-2 kv_full[3]  3-5 kv_empty[3]  6,7 s_full[2]  8,9 p_full[2]  10 pv_done  11 q_ready
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tail);
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(tail + 128);
+  int* stab = reinterpret_cast<int*>(tail + 256);                      // this window's token table, staged once
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int* ktab = p.key_tok + (long)win * p.NKO;
   const int hoff = head * 128;
@@ -98,111 +116,122 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
   auto bar = [&](int i) { return b0 + 8u * (uint32_t)i; };
 
   if (tid == 0) {
-    ua_bar_init(bar(0), 128); ua_bar_init(bar(1), 128);        // kv_full: every producer thread arrives
-    ua_bar_init(bar(2), 1); ua_bar_init(bar(3), 1);            // kv_empty: tcgen05.commit
-    ua_bar_init(bar(4), 1); ua_bar_init(bar(5), 1);            // s_full: tcgen05.commit
-    ua_bar_init(bar(6), 128); ua_bar_init(bar(7), 128);        // p_full: every softmax thread arrives
-    ua_bar_init(bar(8), 1);                                    // pv_done: tcgen05.commit
+    for (int i = 0; i < UA_STAGES; ++i) { ua_bar_init(bar(i), 128); ua_bar_init(bar(3 + i), 1); }   // kv_full: producer threads; kv_empty: commit
+    ua_bar_init(bar(6), 1); ua_bar_init(bar(7), 1);            // s_full: tcgen05.commit
+    ua_bar_init(bar(8), 128); ua_bar_init(bar(9), 128);        // p_full: every softmax thread arrives
+    ua_bar_init(bar(10), 1);                                   // pv_done: tcgen05.commit
+    ua_bar_init(bar(11), 128);                                 // q_ready: softmax threads wrote Q into TMEM
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ua_smem(&tmem_base_s)), "r"(512));
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ua_smem(tmem_base_p)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // ---- query tile -> shared memory (K-major SW128), pre-scaled into the log2 domain
-  for (int idx = tid; idx < UA_BM * 32; idx += UA_THREADS) {
-    const int row = idx >> 5, c4 = idx & 31;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < nq) {
-      const int qi = q0 + row, fr = qi / p.WN, tok = ktab[qi - fr * p.WN];
-      v = *reinterpret_cast<const float4*>(p.qkv + ((long)fr * p.NT + tok) * p.ld_qkv + hoff + c4 * 4);
-    }
-    v.x *= p.scale_log2; v.y *= p.scale_log2; v.z *= p.scale_log2; v.w *= p.scale_log2;
-    *reinterpret_cast<float4*>(sQ + ua_off(row, c4 * 4, UA_BM)) = v;
-  }
+  for (int i = tid; i < p.NKO; i += UA_THREADS) stab[i] = ktab[i];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tbase = tmem_base_s;
-  const uint32_t tO = tbase, tS0 = tbase + 128, tP0 = tbase + 256;      // O: 128 cols; S: 2 x 64; P: 2 x 64
+  const uint32_t tbase = *tmem_base_p;
+  const uint32_t tO = tbase, tS0 = tbase + 128, tP0 = tbase + 256, tQ = tbase + 384;   // O 128 | S 2x64 | P 2x64 | Q 128 columns
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 12) {
     // ================================================= producers: K tile (cp.async) + V^T tile (transposing stores)
-    const int ptid = tid - 128;
-    for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1, use = j >> 1;
-      ua_bar_wait(bar(2 + s), (use & 1) ^ 1);                            // stage free (passes immediately on first use)
-      uint8_t* sK = base + UA_Q_BYTES + s * UA_STAGE_BYTES;
+    // two groups of 4 warps fill alternate tiles, so one group's global-load latency hides behind the other's stores
+    const int grp = (warp - 4) >> 2, ptid = (tid - 128) & 127;
+    for (int j = grp; j < ntiles; j += 2) {
+      const int s = j % UA_STAGES, use = j / UA_STAGES;
+      ua_bar_wait(bar(3 + s), (use & 1) ^ 1);                            // stage free (passes immediately on first use)
+      uint8_t* sK = base + s * UA_STAGE_BYTES;
       uint8_t* sV = sK + UA_K_BYTES;
-      // K: 64 keys x 32 chunks of 16 B
-      for (int idx = ptid; idx < UA_BN * 32; idx += 128) {
-        const int key = idx >> 5, c4 = idx & 31, jk = j * UA_BN + key;
-        uint8_t* dst = sK + ua_off(key, c4 * 4, UA_BN);
-        if (jk < nkeys) {
-          const int kfi = jk / keys_per_frame, slot = jk - kfi * keys_per_frame, fr = p.kf_start + kfi * p.kf_step;
-          const float* src = slot < p.NKO ? p.qkv + ((long)fr * p.NT + ktab[slot]) * p.ld_qkv + p.C + hoff
-                                          : p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + hoff;
-          pp_cp_async16(dst, src + c4 * 4);
-        } else {
-          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      pp_cp_async_commit();
-      // V^T: thread <-> (key, half of the head dims); for a fixed dim the 32 lanes (keys) hit 32 distinct banks
-      {
-        const int key = ptid & 63, half = ptid >> 6, jk = j * UA_BN + key;
+      // row pointers of the tile's 64 keys (K part; V follows at +C in token rows and pooled rows alike)
+      const float** kp = reinterpret_cast<const float**>(tail + 1152) + s * UA_BN;        // per stage
+      if (ptid < UA_BN) {
+        const int jk = j * UA_BN + ptid;
         const float* src = nullptr;
         if (jk < nkeys) {
           const int kfi = jk / keys_per_frame, slot = jk - kfi * keys_per_frame, fr = p.kf_start + kfi * p.kf_step;
-          src = slot < p.NKO ? p.qkv + ((long)fr * p.NT + ktab[slot]) * p.ld_qkv + 2 * p.C + hoff
-                             : p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + p.C + hoff;
+          src = slot < p.NKO ? p.qkv + ((long)fr * p.NT + stab[slot]) * p.ld_qkv + p.C + hoff
+                             : p.pool + ((long)fr * p.NP + (slot - p.NKO)) * p.ld_pool + hoff;
         }
+        kp[ptid] = src;
+      }
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // this producer group only
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      // K and V rows: a warp copies whole 512-byte rows (lane <-> 16-byte chunk, 4 cache lines per instruction);
+      // K goes straight into its swizzled tile, V into this group's row-major staging buffer
+      float* stg = reinterpret_cast<float*>(stg_base + grp * UA_STG_BYTES);
 #pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int kk = (ptid >> 5) + 4 * i, c4 = ptid & 31;
+        const float* src = kp[kk];
+        uint8_t* dk = sK + ua_off(kk, c4 * 4, UA_BN);
+        float* dv = stg + kk * UA_LDSTG + c4 * 4;
+        if (src) { pp_cp_async16(dk, src + c4 * 4); pp_cp_async16(dv, src + p.C + c4 * 4); }
+        else {
+          *reinterpret_cast<float4*>(dk) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dv) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      pp_cp_async_commit();
+      pp_cp_async_wait<0>();
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // every thread's copies have landed
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      // V^T: thread <-> (key, half of the head dims).  LDS.128 by key is conflict-free (row stride 132 floats); for a
+      // fixed dim the 32 lanes (= 32 consecutive keys) store to 32 distinct banks of the swizzled tile
+      {
+        const int key = ptid & 63, half = ptid >> 6;
+        const float* vr = stg + key * UA_LDSTG + half * 64;
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(vr + i * 4);
           const int d = half * 64 + i * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (src) v = *reinterpret_cast<const float4*>(src + d);
           *reinterpret_cast<float*>(sV + ua_off(d + 0, key, 128)) = v.x;
           *reinterpret_cast<float*>(sV + ua_off(d + 1, key, 128)) = v.y;
           *reinterpret_cast<float*>(sV + ua_off(d + 2, key, 128)) = v.z;
           *reinterpret_cast<float*>(sV + ua_off(d + 3, key, 128)) = v.w;
         }
       }
-      pp_cp_async_wait<0>();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
-      ua_bar_arrive(bar(0 + s));
+      ua_bar_arrive(bar(s));
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ================================================= MMA issuer (one elected thread)
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
-      const uint32_t qaddr = ua_smem(sQ);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        ua_bar_wait(bar(0 + s), (j >> 1) & 1);                           // K/V tile j landed
+      auto issue_s = [&](int j) {                                        // caller has observed kv_full for tile j
+        const int sb = j & 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t kaddr = ua_smem(base + UA_Q_BYTES + s * UA_STAGE_BYTES);
+        const uint32_t kaddr = ua_smem(base + (j % UA_STAGES) * UA_STAGE_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)                                   // 128 head dims = 4 k-blocks x 4 k-steps of 8
-          ua_mma_ss(tS0 + s * UA_BN, ua_desc(qaddr + (ks >> 2) * (UA_BM * 128) + (ks & 3) * 32),
-                    ua_desc(kaddr + (ks >> 2) * (UA_BN * 128) + (ks & 3) * 32), idesc_s, ks > 0);
-        ua_commit(bar(4 + s));                                           // S_j ready for the softmax warps
+        for (int ks = 0; ks < 16; ++ks)                                   // 128 head dims = 4 k-blocks x 4 k-steps of 8; A = Q from TMEM
+          ua_mma_ts(tS0 + sb * UA_BN, tQ + ks * 8, ua_desc(kaddr + (ks >> 2) * (UA_BN * 128) + (ks & 3) * 32), idesc_s, ks > 0);
+        ua_commit(bar(6 + sb));                                          // S_j ready for the softmax warps
       };
-      issue_s(0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        if (j + 1 < ntiles) issue_s(j + 1);                              // S buffer (j+1)&1 is free: P_{j-1} was consumed by PV_{j-1}
-        ua_bar_wait(bar(6 + s), (j >> 1) & 1);                           // P_j written (and O rescaled if needed)
+      auto issue_pv = [&](int j) {
+        const int sb = j & 1, st = j % UA_STAGES;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t vaddr = ua_smem(base + UA_Q_BYTES + s * UA_STAGE_BYTES + UA_K_BYTES);
+        const uint32_t vaddr = ua_smem(base + st * UA_STAGE_BYTES + UA_K_BYTES);
 #pragma unroll
         for (int ks = 0; ks < UA_BN / 8; ++ks)                            // 64 keys = 2 k-blocks x 4 k-steps
-          ua_mma_ts(tO, tP0 + s * UA_BN + ks * 8, ua_desc(vaddr + (ks >> 2) * (128 * 128) + (ks & 3) * 32), idesc_o,
+          ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, ua_desc(vaddr + (ks >> 2) * (128 * 128) + (ks & 3) * 32), idesc_o,
                     (j > 0 || ks > 0));
-        ua_commit(bar(2 + s));                                           // stage s may be refilled
-        ua_commit(bar(8));                                               // O holds tiles 0..j
+        ua_commit(bar(3 + st));                                          // stage may be refilled
+        ua_commit(bar(10));                                              // O holds tiles 0..j
+      };
+      ua_bar_wait(bar(11), 0);                                           // Q is in TMEM
+      ua_bar_wait(bar(0), 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        // issue whichever is ready first: S_{j+1} (needs K/V tile j+1; its S buffer is free since P_{j-1} was consumed)
+        // or P_j.V_j (needs the softmax warps' P_j, and O rescaled if that was required)
+        bool s_done = j + 1 >= ntiles, pv_done = false;
+        for (long spin = 0; !(s_done && pv_done); ++spin) {
+          if (!s_done && ua_bar_test(bar((j + 1) % UA_STAGES), (((j + 1) / UA_STAGES) & 1))) { issue_s(j + 1); s_done = true; }
+          if (!pv_done && ua_bar_test(bar(8 + (j & 1)), (j >> 1) & 1)) { issue_pv(j); pv_done = true; }
+          if (spin > (1L << 26)) __trap();
+        }
       }
     }
   } else {
@@ -210,9 +239,27 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
     const int row = warp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     float m_used = -INFINITY, l = 0.f;
+    {   // this thread's query row -> TMEM lane `row`, columns tQ..tQ+127 (A operand of S = Q K^T), pre-scaled into the log2 domain
+      const float* qrow = nullptr;
+      if (row < nq) { const int qi = q0 + row, fr = qi / p.WN; qrow = p.qkv + ((long)fr * p.NT + stab[qi - fr * p.WN]) * p.ld_qkv + hoff; }
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t qv[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 v = qrow ? *reinterpret_cast<const float4*>(qrow + c0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          qv[c] = __float_as_uint(v.x * p.scale_log2); qv[c + 1] = __float_as_uint(v.y * p.scale_log2);
+          qv[c + 2] = __float_as_uint(v.z * p.scale_log2); qv[c + 3] = __float_as_uint(v.w * p.scale_log2);
+        }
+        UA_ST32(tQ + c0 + lane_off, qv);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      ua_bar_arrive(bar(11));
+    }
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
-      ua_bar_wait(bar(4 + s), (j >> 1) & 1);
+      ua_bar_wait(bar(6 + s), (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v0[32], v1[32];
       UA_LD32(tS0 + s * UA_BN + lane_off, v0);
@@ -220,20 +267,22 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int kbase = j * UA_BN;
       float mx = -INFINITY;
+      if (kbase + UA_BN > nkeys) {                                        // ragged last tile: mask the missing keys
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float a = kbase + c < nkeys ? __uint_as_float(v0[c]) : -INFINITY;
-        float b = kbase + 32 + c < nkeys ? __uint_as_float(v1[c]) : -INFINITY;
-        v0[c] = __float_as_uint(a); v1[c] = __float_as_uint(b);
-        mx = fmaxf(mx, fmaxf(a, b));
+        for (int c = 0; c < 32; ++c) {
+          if (kbase + c >= nkeys) v0[c] = 0xff800000u;
+          if (kbase + 32 + c >= nkeys) v1[c] = 0xff800000u;
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c])));
       // lazy rescaling: keep the running reference maximum unless some row grew by more than 2^8
       const bool grow = mx > m_used + 8.0f;
       if (__any_sync(0xffffffffu, grow)) {
         const float m_new = grow ? mx : m_used;
-        const float alpha = exp2f(m_used - m_new);                        // m_used = -inf on the first tile -> alpha = 0
+        const float alpha = ua_ex2(m_used - m_new);                       // m_used = -inf on the first tile -> alpha = 0
         if (j > 0) {
-          ua_bar_wait(bar(8), (j - 1) & 1);                               // PV_{j-1} finished: O is quiescent
+          ua_bar_wait(bar(10), (j - 1) & 1);                              // PV_{j-1} finished: O is quiescent
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
           for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -251,7 +300,7 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float a = exp2f(__uint_as_float(v0[c]) - m_used), b = exp2f(__uint_as_float(v1[c]) - m_used);
+        const float a = ua_ex2(__uint_as_float(v0[c]) - m_used), b = ua_ex2(__uint_as_float(v1[c]) - m_used);
         rs += a + b;
         v0[c] = __float_as_uint(a); v1[c] = __float_as_uint(b);
       }
@@ -260,14 +309,14 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       UA_ST32(tP0 + s * UA_BN + 32 + lane_off, v1);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      ua_bar_arrive(bar(6 + s));
+      ua_bar_arrive(bar(8 + s));
     }
     // ---- epilogue: O / l -> global
-    ua_bar_wait(bar(8), (ntiles - 1) & 1);
+    ua_bar_wait(bar(10), (ntiles - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = 1.0f / l;
     float* orow = nullptr;
-    if (row < nq) { const int qi = q0 + row, fr = qi / p.WN; orow = p.out + ((long)fr * p.NT + ktab[qi - fr * p.WN]) * p.ld_out + hoff; }
+    if (row < nq) { const int qi = q0 + row, fr = qi / p.WN; orow = p.out + ((long)fr * p.NT + stab[qi - fr * p.WN]) * p.ld_out + hoff; }
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t o[32];
@@ -283,11 +332,12 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
 // masked windows on tcgen05; called by pp_sparse_window_attn (mma_kernels.cu)
 int pp_launch_sparse_attn_umma(const PPAttnParams& p, int n_windows, cudaStream_t stream) {
+  if (p.NKO > 224) return PP_ERR_SHAPE;
   if (cudaFuncSetAttribute(k_sparse_attn_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES) != cudaSuccess)
     return PP_ERR_LAUNCH;
   dim3 grid((p.t * p.WN + UA_BM - 1) / UA_BM, p.C / 128, n_windows);
