@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
         for (int i = 0; i < 16; ++i) {
           const float4 v = *reinterpret_cast<const float4*>(vr + i * 4);
           const int d = half * 64 + i * 4;
-          *reinterpret_cast<float*>(sV + ua_off(d + 0, key, 128)) = v.x;
-          *reinterpret_cast<float*>(sV + ua_off(d + 1, key, 128)) = v.y;
-          *reinterpret_cast<float*>(sV + ua_off(d + 2, key, 128)) = v.z;
-          *reinterpret_cast<float*>(sV + ua_off(d + 3, key, 128)) = v.w;
+          *reinterpret_cast<uint32_t*>(sV + ua_off(d + 0, key, 128)) = pp_tf32(v.x);
+          *reinterpret_cast<uint32_t*>(sV + ua_off(d + 1, key, 128)) = pp_tf32(v.y);
+          *reinterpret_cast<uint32_t*>(sV + ua_off(d + 2, key, 128)) = pp_tf32(v.z);
+          *reinterpret_cast<uint32_t*>(sV + ua_off(d + 3, key, 128)) = pp_tf32(v.w);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
@@ -248,8 +248,9 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 v = qrow ? *reinterpret_cast<const float4*>(qrow + c0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          qv[c] = __float_as_uint(v.x * p.scale_log2); qv[c + 1] = __float_as_uint(v.y * p.scale_log2);
-          qv[c + 2] = __float_as_uint(v.z * p.scale_log2); qv[c + 3] = __float_as_uint(v.w * p.scale_log2);
+          // round-to-nearest TF32 here: the tensor core would otherwise truncate the fp32 mantissa
+          qv[c] = pp_tf32(v.x * p.scale_log2); qv[c + 1] = pp_tf32(v.y * p.scale_log2);
+          qv[c + 2] = pp_tf32(v.z * p.scale_log2); qv[c + 3] = pp_tf32(v.w * p.scale_log2);
         }
         UA_ST32(tQ + c0 + lane_off, qv);
       }
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       for (int c = 0; c < 32; ++c) {
         const float a = ua_ex2(__uint_as_float(v0[c]) - m_used), b = ua_ex2(__uint_as_float(v1[c]) - m_used);
         rs += a + b;
-        v0[c] = __float_as_uint(a); v1[c] = __float_as_uint(b);
+        v0[c] = pp_tf32(a); v1[c] = pp_tf32(b);
       }
       l += rs;
       UA_ST32(tP0 + s * UA_BN + lane_off, v0);

@@ -23,6 +23,10 @@ class InferenceConfig:
     ref_stride: int = 10
     neighbor_length: int = 10
     subvideo_length: int = 80
+    # frames per RAFT call.  None = as many as an 8 GB correlation pyramid allows (never fewer than the reference's
+    # 12/8/4/2, inference_propainter.py:302-309).  Frame pairs are independent, so this only changes batching.
+    raft_clip_frames: int = None
+    windows_in_flight: int = 2      # generator windows computed concurrently on separate streams (compositing stays ordered)
 
 
 def get_ref_index(mid_neighbor_id, neighbor_ids, length, ref_stride=10, ref_num=-1):
@@ -93,9 +97,14 @@ class ProPainterPipeline:
 
     # ---- stage 1 (:302-330)
     def compute_flows(self, frames, cfg):
-        T, W = frames.shape[1], frames.shape[-1]
+        T, H, W = frames.shape[1], frames.shape[-2], frames.shape[-1]
+        clip = cfg.raft_clip_frames
+        if clip is None:
+            n = (H // 8) * (W // 8)
+            pairs = int(8e9 // (5.4 * n * n))                         # 4 pyramid levels ~ 1.34 N^2 floats per pair
+            clip = max(raft_clip_len(W), min(T, pairs // 2 + 1))
         ff, bb = [], []
-        for s, e in flow_chunks(T, raft_clip_len(W)):
+        for s, e in flow_chunks(T, clip):
             f, b = self.fix_raft(frames[:, s:e], iters=cfg.raft_iter)
             ff.append(f)
             bb.append(b)
@@ -143,15 +152,44 @@ class ProPainterPipeline:
         md = masks_dilated[0].contiguous()
         # encoder features depend only on (frame, mask, updated mask): computed once per clip, not once per window
         enc_all = self.model.encode(upd_frames[0], md, upd_masks[0])
-        for wi, (nb, refs) in enumerate(plan):
-            if windows is not None and wi not in windows:
-                continue
+        todo = [(wi, nb, refs) for wi, (nb, refs) in enumerate(plan) if windows is None or wi in windows]
+        nfl = max(1, int(cfg.windows_in_flight)) if upd_frames.is_cuda else 1
+        if nfl == 1:
+            for wi, nb, refs in todo:
+                ids = nb + refs
+                pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                                                   md[ids], upd_masks[0, ids], len(nb))
+                ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
+                for i in nb:
+                    visited[i] = True
+            return comp
+        # windows are independent given the stage-3 outputs: keep `nfl` of them in flight on side streams (each slot owns
+        # its own captured graph instance); compositing is replayed on the main stream in ascending window order because
+        # the 1/2-1/2 blend of inference_propainter.py:445-450 is order-dependent
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side_streams") or len(self._side_streams) < nfl:
+            self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(nfl)]
+        pending = []
+
+        def drain(k):
+            while len(pending) > k:
+                slot, nb, pred = pending.pop(0)
+                main.wait_stream(self._side_streams[slot])
+                pred.record_stream(main)
+                ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
+                for i in nb:
+                    visited[i] = True
+        for n, (wi, nb, refs) in enumerate(todo):
+            slot = n % nfl
+            drain(nfl - 1)
             ids = nb + refs
-            pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
-                                               md[ids], upd_masks[0, ids], len(nb))
-            ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
-            for i in nb:
-                visited[i] = True
+            st = self._side_streams[slot]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                                                   md[ids], upd_masks[0, ids], len(nb), slot=slot)
+            pending.append((slot, nb, pred))
+        drain(0)
         return comp
 
     # ---- whole path

@@ -148,11 +148,12 @@ class InpaintGenerator(ParamNet):
 
     @torch.no_grad()
     def forward_features(self, enc_feat, completed_flows, masks_in, masks_updated, num_local_frames,
-                         interpolation="bilinear", t_dilation=2):
+                         interpolation="bilinear", t_dilation=2, slot=0):
         """``forward`` minus the encoder: enc_feat [t,128,h,w] (local frames first), flows 2x[lt-1,2,H,W],
-        masks [t,1,H,W] -> [lt,3,H,W]."""
+        masks [t,1,H,W] -> [lt,3,H,W].  `slot` selects an independent captured-graph instance so that several
+        windows can be in flight on different streams."""
         lt = num_local_frames
-        return self.graphs(("gen_feat", lt, interpolation, t_dilation),
+        return self.graphs(("gen_feat", lt, interpolation, t_dilation, slot),
                            lambda *a: self._forward_features(*a, lt, interpolation, t_dilation),
                            enc_feat.contiguous(memory_format=torch.channels_last), completed_flows[0].contiguous().float(),
                            completed_flows[1].contiguous().float(), masks_in.contiguous().float(),
