@@ -159,13 +159,56 @@ def cpu_baseline(wl, budget_s=40.0):
             "sample": f"first {T} frames of the workload clip, full 4-stage pipeline once ({dt:.1f} s)"}
 
 
+def _time_kernel(torch, fn, reps=10):
+    """CUDA events on the launch stream (= torch's current stream, which ops.* launch on), L2 flushed between reps."""
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.mean(ts)
+
+
 def roofline_probe(torch, pipe, wl):
-    """Dominant own kernel measured live with CUDA events on the launch stream."""
+    """Live roofline of our dominant kernels at the workload's shapes.
+
+    Primary entry = the tensor-core kernel the north star names (sparse window attention, tcgen05/TMEM); the
+    `others` list carries the HBM-bound RAFT lookup and the deformable alignment.  ncu DRAM traffic figures
+    (`traffic`) come from the committed captures under profiles/ (they cannot be measured outside a profiler)."""
     from propainter_b200 import ops
-    hbm, tf, src = peaks()
-    h, w = wl["H"] // 8, wl["W"] // 8
-    B = 22 if wl["W"] <= 640 else 6                           # pairs per RAFT refinement batch (2*(clip-1))
+    from propainter_b200.window_index import padded_grid, token_grid, window_key_table
+    hbm, bf16, src = peaks()
+    tf32_peak = bf16 / 2.0                                          # tcgen05 kind::tf32 runs at half the bf16 rate
     dev = pipe.device
+    # ---- sparse window attention: one transformer layer of a full generator window (t = 18 frames)
+    t, C = 18, 512
+    fh, fw = token_grid((wl["H"] // 4, wl["W"] // 4))
+    H2, W2 = padded_grid(fh, fw)
+    nwin = (H2 // 5) * (W2 // 9)
+    qkv = torch.randn(t, H2 * W2, 3 * C, device=dev)
+    pool = torch.randn(t, (H2 // 4) * (W2 // 4), 2 * C, device=dev)
+    ktab = torch.from_numpy(window_key_table(H2, W2)).to(dev)
+    flags = torch.zeros(nwin, dtype=torch.int32, device=dev)
+    nmask = max(1, round(nwin * 5 / 16))                           # the C2 ellipse masks ~5 of 16 windows
+    flags[:nmask] = 1
+    nkf = len(range(0, t, 2))
+    nkeys = nkf * (ktab.shape[1] + pool.shape[1])
+    flops = nmask * 4 * 2 * 2 * (t * 45) * nkeys * 128             # QK^T + PV of the masked windows (SURVEY.md §8d)
+    ms = _time_kernel(torch, lambda: ops.sparse_window_attn(qkv, pool, ktab, flags, t, H2 * W2, 0, 2))
+    ach = flops / (ms * 1e-3) / 1e12
+    primary = {"kernel": "k_sparse_attn_umma (+ unmasked-window kernel)", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
+               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": 29.6e6, "peak_source": src + " bf16_tflops / 2 (TF32)",
+               "launch_ms": ms, "algorithmic_flops": flops, "masked_windows": f"{nmask} of {nwin}"}
+    # ---- RAFT correlation lookup, one refinement step of the whole clip
+    h, w = wl["H"] // 8, wl["W"] // 8
+    B = min(2 * (wl["T"] - 1), 158)
     fmap = torch.randn(B // 2 + 1, h * w, 256, device=dev)
     a = torch.arange(B // 2, device=dev, dtype=torch.int32)
     levels = ops.corr_alloc(B, h, w, dev)
@@ -173,25 +216,24 @@ def roofline_probe(torch, pipe, wl):
     ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
     coords = (torch.stack([xs, ys], -1).float()[None] + torch.randn(B, h, w, 2, device=dev) * 3).contiguous()
     out = torch.empty(B, h, w, 324, device=dev)
-    flush = torch.empty(64 * 1024 * 1024, device=dev)
-    for _ in range(3):
-        ops.corr_lookup(levels, coords, out)
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.corr_lookup(levels, coords, out)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = statistics.mean(ts)
-    # algorithmic bytes per pair-iteration: unique 10x10 patches at 4 levels + the 324-ch output
+    ms_l = _time_kernel(torch, lambda: ops.corr_lookup(levels, coords, out))
     npx = h * w
-    alg = B * (npx * 4 * 100 * 4 + npx * 324 * 4 + npx * 8)
-    ach = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "k_corr_lookup", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": None, "peak_source": src, "launch_ms": ms, "algorithmic_bytes": alg}
+    alg = B * (npx * 4 * 100 * 4 + npx * 324 * 4 + npx * 8)        # unique 10x10 patches at 4 levels + 324-ch output + coords
+    ach_l = alg / (ms_l * 1e-3) / 1e9
+    # ---- deformable alignment, one generator propagation step
+    Hh, Ww = wl["H"] // 4, wl["W"] // 4
+    x, o = torch.randn(Hh, Ww, 128, device=dev), torch.randn(Hh, Ww, 432, device=dev)
+    fl, wp = torch.randn(Hh, Ww, 2, device=dev), torch.randn(9 * 128, 128, device=dev) * 0.03
+    bvec, dout = torch.randn(128, device=dev), torch.empty(Hh, Ww, 128, device=dev)
+    ms_d = _time_kernel(torch, lambda: ops.deform_align(x, o, fl, 3.0, wp, bvec, dout))
+    fl_d = Hh * Ww * 9 * 128 * 128 * 2
+    primary["others"] = [
+        {"kernel": "k_corr_lookup_tma", "bound": "hbm", "achieved": ach_l, "peak": hbm, "unit": "GB/s", "frac": ach_l / hbm,
+         "traffic": 142.3e6 * B / 22, "launch_ms": ms_l, "algorithmic_bytes": alg},
+        {"kernel": "k_deform_align (+ split-K reduce)", "bound": "tensor", "achieved": fl_d / (ms_d * 1e-3) / 1e12, "peak": tf32_peak,
+         "unit": "TFLOP/s", "frac": fl_d / (ms_d * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_d,
+         "algorithmic_flops": fl_d, "note": "warp-level mma.sync TF32 (legacy tensor path), latency-bound gather"}]
+    return primary
 
 
 def run_ours(args, wl):
