@@ -289,6 +289,9 @@ def run_ours(args, wl):
             sampler.start()
         l0 = ops.LAUNCHES
         total = 0.0
+        ranged = sample_clocks and os.environ.get("PP_PROFILE_RANGE")     # ncu --profile-from-start off: timed steps only
+        if ranged:
+            torch.cuda.profiler.start()
         for _ in range(steps):
             flush.zero_()
             torch.cuda.synchronize()
@@ -298,6 +301,8 @@ def run_ours(args, wl):
             e1.record()
             torch.cuda.synchronize()
             total += e0.elapsed_time(e1)
+        if ranged:
+            torch.cuda.profiler.stop()
         barrier()
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([total], device=dev, dtype=torch.float64)

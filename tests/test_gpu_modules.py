@@ -172,3 +172,40 @@ def test_pipeline_shipping_defaults_vs_golden_and_oracle():
     psnr = ops_ref.psnr_u8(a, g["comp"])
     print(f"shipping defaults vs reference golden: PSNR {psnr:.2f} dB, max diff {np.abs(a.astype(int) - g['comp'].astype(int)).max()}")
     assert psnr > 40.0
+
+
+def test_weight_reload_drops_captured_graphs():
+    """load_state_dict / .to() must invalidate packed weights and captured CUDA graphs (drop-in semantics)."""
+    from propainter_b200.model.recurrent_flow_completion import RecurrentFlowCompleteNet
+    net = RecurrentFlowCompleteNet(None, seed=2).to(DEV)
+    other = RecurrentFlowCompleteNet(None, seed=7)
+    gen = torch.Generator().manual_seed(5)
+    T, H, W = 4, 64, 64
+    flows = torch.randn(1, T, 2, H, W, generator=gen)
+    masks = torch.zeros(1, T, 1, H, W)
+    masks[..., 16:40, 20:44] = 1
+    a1, _ = net(flows.to(DEV), masks.to(DEV))
+    a2, _ = net(flows.to(DEV), masks.to(DEV))                       # replay
+    assert torch.equal(a1, a2)
+    net.load_state_dict(other.state_dict(), strict=True)
+    b, _ = net(flows.to(DEV), masks.to(DEV))
+    ref = flowcomp_ref.rfc_forward(cpu_sd(other), flows, masks)
+    assert rel_err(b.cpu(), ref) < 1e-2 and rel_err(a1.cpu(), ref) > 5e-2
+
+
+@pytest.mark.shipping
+def test_pipeline_720p_and_border_mask():
+    """BASELINE configs[3]/[2] shapes on one GPU (short clips): 1280x720 object removal and a 25 % border mask
+    (every attention window masked), shipping defaults, vs the CPU oracle."""
+    from propainter_b200 import synth
+    from propainter_b200.inference_propainter import InferenceConfig, ProPainterPipeline
+    pipe = ProPainterPipeline(device=DEV)
+    sds = {k: {n: v.detach().cpu() for n, v in sd.items()} for k, sd in pipe.state_dicts().items()}
+    for (T, H, W, mask) in ((5, 720, 1280, "ellipse"), (7, 240, 432, "border")):
+        u8, fm, md = synth.make_clip(T, H, W, mask=mask, seed=1)
+        cfg = InferenceConfig(raft_iter=2)
+        comp = pipe(torch.from_numpy(u8), fm, md, cfg).cpu().numpy()
+        ref = pipeline_ref.run_pipeline(sds, u8, fm, md, raft_iter=2)
+        psnr = ops_ref.psnr_u8(comp, ref)
+        print(f"{W}x{H} T={T} mask={mask}: PSNR {psnr:.2f} dB vs oracle")
+        assert psnr > 40.0
