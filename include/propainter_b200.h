@@ -122,6 +122,9 @@ int pp_bias_act(float* x, const float* bias, long n_pix, int C, int act, float s
 int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h, int w, int C, cudaStream_t stream);
 
 /* ---- driver-side pixel ops (inference_propainter.py) ----------------------------------------- */
+/* read_mask's scipy.ndimage.binary_dilation(mask, iterations=k) (cross structure) + to_tensors (inference_propainter.py:93-107,
+ * :265-266): uint8 masks [T][H][W] (non-zero = hole) -> float {0,1} [T][1][H][W]; iterations = 0 only binarises. */
+int pp_mask_dilate(const uint8_t* src, float* dst, int T, int H, int W, int iterations, cudaStream_t stream);
 /* to_tensors()(frames)*2-1  core/utils.py:130-170 + inference_propainter.py:264: uint8 [T][H][W][3] -> planar float */
 int pp_u8_to_frames(const uint8_t* src, float* dst, int T, int H, int W, cudaStream_t stream);
 #define PP_MAX_WINDOW 32

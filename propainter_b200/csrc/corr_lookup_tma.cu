@@ -1,7 +1,7 @@
 // RAFT correlation lookup, TMA-staged (sm_100a).
 //
 // One warp per source pixel.  For each of the 4 pyramid levels the warp's elected lane issues one
-// cp.async.bulk.tensor (TMA, 3-D tiled: x, y, plane) that lands the 12x12 neighbourhood of the lookup
+// cp.async.bulk.tensor (TMA, 3-D tiled: x, y, plane) that lands the 16x10 neighbourhood of the lookup
 // centre in shared memory (the box's innermost coordinate is rounded down to a multiple of 4 floats: a
 // tiled TMA load whose first element is not 16-byte aligned faults with "illegal instruction" -- measured
 // with profiles/probes/tma_probe.cu); out-of-range rows / columns are zero-filled by the TMA unit, which *is*
@@ -13,10 +13,10 @@
 #include "../../include/propainter_b200.h"
 
 #define LK_WARPS 8
-#define LK_BOX 12                       // rows of the staged box
-#define LK_BOXW 16                      // columns: 12 needed + up to 3 because the box must start 16-byte aligned
-#define LK_HALF 5
-#define LK_LVL_FLOATS (LK_BOX * LK_BOXW) // 768 B per level: every box stays 128-byte aligned in shared memory
+#define LK_BOX 10                       // rows of the staged box: taps b = 0..8 read rows b and b+1
+#define LK_BOXW 16                      // columns: 10 needed + up to 3 because the box must start 16-byte aligned
+#define LK_HALF 4
+#define LK_LVL_FLOATS 192               // 640 B box + pad: level l's box starts 768 B (+0 banks) after level l-1's
 
 __device__ __forceinline__ uint32_t lk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_LVL_FLOATS * 4) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_BOX * LK_BOXW * 4) : "memory");
     const CUtensorMap* tms[4] = {&tm0, &tm1, &tm2, &tm3};
 #pragma unroll
     for (int l = 0; l < 4; ++l)
@@ -60,24 +60,34 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_
     if (!done) __trap();
   }
   float* o = out + pix * 324;
+  // Register-blocked along y: a lane owns one (level, x-tap a) column and slides down the 10 staged rows, so each
+  // shared-memory value is read once per column pair (20 loads for 9 taps instead of 36) and the 9 results of a lane
+  // are 9 consecutive output floats (index l*81 + a*9 + b).  Pass 0: levels 0-2 (27 lanes), pass 1: level 3 (9 lanes).
+  // All taps of a level share the fractional part of the centre (integer tap offsets): corners outside the image read
+  // the zeros TMA filled in.  (The reference sends every tap through grid_sample's normalise / un-normalise round trip,
+  // RAFT/utils/utils.py:60-65, which only adds ~1e-6 px of rounding noise -- dropped, well inside the 1e-4 tolerance.)
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    // All 81 taps of a level share the fractional part of the centre (integer tap offsets), so the
-    // weights are computed once; corners outside the image read the zeros TMA filled in.  (The reference
-    // sends each tap through grid_sample's normalise/un-normalise round trip, RAFT/utils/utils.py:60-65,
-    // which only adds ~1e-6 px of rounding noise -- dropped here, well inside the 1e-4 parity tolerance.)
-    const float* P = &patch[warp][l][0];
-    const float inv = 1.0f / (float)(1 << l);
-    const float xl = cx * inv, yl = cy * inv;
-    const float fxl = floorf(xl), fyl = floorf(yl);
-    const bool sane = fabsf(xl) < 1.0e6f && fabsf(yl) < 1.0e6f;
-    const float wx1 = sane ? xl - fxl : 0.f, wy1 = sane ? yl - fyl : 0.f;
-    const float wx0 = sane ? 1.0f - wx1 : 0.f, wy0 = sane ? 1.0f - wy1 : 0.f;
-    const int ox = lk_base(cx, inv) + 1 - bx[l], oy = 1;        // box position of tap (0,0)'s top-left corner
-    for (int tap = lane; tap < 81; tap += 32) {
-      const int a = tap / 9, b = tap - a * 9;                    // a moves x, b moves y (RAFT/corr.py:38-44)
-      const float* q = P + (oy + b) * LK_BOXW + ox + a;
-      o[l * 81 + tap] = wy0 * (wx0 * q[0] + wx1 * q[1]) + wy1 * (wx0 * q[LK_BOXW] + wx1 * q[LK_BOXW + 1]);
+  for (int pass = 0; pass < 2; ++pass) {
+    const int l = pass == 0 ? lane / 9 : 3, a = pass == 0 ? lane - 9 * (lane / 9) : lane;
+    const bool act = pass == 0 ? lane < 27 : lane < 9;
+    if (act) {
+      const float inv = 1.0f / (float)(1 << l);
+      const float xl = cx * inv, yl = cy * inv;
+      const bool sane = fabsf(xl) < 1.0e6f && fabsf(yl) < 1.0e6f;
+      const float wx1 = sane ? xl - floorf(xl) : 0.f, wy1 = sane ? yl - floorf(yl) : 0.f;
+      const float wx0 = sane ? 1.0f - wx1 : 0.f, wy0 = sane ? 1.0f - wy1 : 0.f;
+      int bxl = bx[0];
+      if (l == 1) bxl = bx[1]; else if (l == 2) bxl = bx[2]; else if (l == 3) bxl = bx[3];
+      const float* q = &patch[warp][l][0] + (lk_base(cx, inv) - bxl) + a;      // row 0 of this lane's column pair
+      float top = wx0 * q[0] + wx1 * q[1];
+      float* ol = o + l * 81 + a * 9;
+#pragma unroll
+      for (int b = 0; b < 9; ++b) {
+        q += LK_BOXW;
+        const float bot = wx0 * q[0] + wx1 * q[1];
+        ol[b] = wy0 * top + wy1 * bot;
+        top = bot;
+      }
     }
   }
 }

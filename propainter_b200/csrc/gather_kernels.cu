@@ -441,6 +441,23 @@ extern "C" int pp_raft_pack_motion(const float* mot, int ld_mot, const float* fl
   return PP_OK;
 }
 
+// ================================================================ mask preparation
+__global__ void __launch_bounds__(256) k_mask_dilate(const uint8_t* __restrict__ src, float* __restrict__ dst, int T, int H,
+                                                     int W, int iterations) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long HW = (long)H * W;
+  if (i >= (long)T * HW) return;
+  const long f = i / HW; const int r = (int)(i - f * HW); const int y = r / W, x = r - y * W;
+  dst[i] = pp_mask_dilate_pixel(src + f * HW, H, W, y, x, iterations);
+}
+// replaces the per-frame scipy.ndimage.binary_dilation + to_tensors of read_mask (inference_propainter.py:93-107, :265-266)
+extern "C" int pp_mask_dilate(const uint8_t* src, float* dst, int T, int H, int W, int iterations, cudaStream_t stream) {
+  if (iterations < 0 || iterations > 64) return PP_ERR_SHAPE;
+  k_mask_dilate<<<pp_blocks((long)T * H * W, 256), 256, 0, stream>>>(src, dst, T, H, W, iterations);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 // ================================================================ frame conversion + compositing
 __global__ void __launch_bounds__(256) k_u8_to_frames(const uint8_t* __restrict__ src, float* __restrict__ dst, int T,
                                                       int H, int W) {

@@ -277,3 +277,19 @@ PP_HD uint8_t pp_composite(float pred, float mask, uint8_t ori, uint8_t prev, in
   float b = PP_ADD(PP_MUL((float)prev, 0.5f), PP_MUL((float)img, 0.5f));
   return (uint8_t)(int)b;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Mask preparation (inference_propainter.py:93-107): scipy.ndimage.binary_dilation with the default cross
+// structure, `iterations` times == union over the L1 ball of that radius; iterations = 0 -> plain binarisation.
+PP_HD float pp_mask_dilate_pixel(const uint8_t* m, int H, int W, int y, int x, int iterations) {
+  for (int dy = -iterations; dy <= iterations; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    const int r = iterations - (dy < 0 ? -dy : dy);
+    for (int dx = -r; dx <= r; ++dx) {
+      const int xx = x + dx;
+      if (xx >= 0 && xx < W && m[(long)yy * W + xx] != 0) return 1.0f;
+    }
+  }
+  return 0.0f;
+}

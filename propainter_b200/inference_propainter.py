@@ -80,6 +80,15 @@ def window_plan(T, cfg):
     return plan
 
 
+def prepare_masks(masks_u8, mask_dilation=4, device="cuda"):
+    """read_mask (inference_propainter.py:77-114) after file I/O: uint8 masks [T,H,W] (or [1,H,W], repeated by the
+    caller) -> (flow_masks, masks_dilated), both float {0,1} [1,T,1,H,W] on the device.  Both use `mask_dilation`
+    (the script passes args.mask_dilation for both, :238-240)."""
+    m = masks_u8.to(device)
+    d = ops.mask_dilate(m, mask_dilation).unsqueeze(0)
+    return d, d.clone()
+
+
 class ProPainterPipeline:
     """RAFT flow -> flow completion -> image propagation -> sliding-window generator -> compositing."""
 

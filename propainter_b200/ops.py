@@ -255,6 +255,16 @@ def upsample2x(x_pm):
     return out
 
 
+def mask_dilate(masks_u8, iterations):
+    """uint8 [T,H,W] (non-zero = hole) -> float {0,1} [T,1,H,W], dilated `iterations` times with the 3x3 cross."""
+    T, H, W = masks_u8.shape
+    out = torch.empty(T, 1, H, W, device=masks_u8.device, dtype=torch.float32)
+    check(_lib.lib().pp_mask_dilate(_p(_dense(masks_u8), torch.uint8), _p(out), T, H, W, int(iterations), _stream()),
+          "pp_mask_dilate")
+    _count(1)
+    return out
+
+
 def u8_to_frames(frames_u8):
     """uint8 [T,H,W,3] -> float planar [T,3,H,W] in [-1,1]."""
     T, H, W, _ = frames_u8.shape

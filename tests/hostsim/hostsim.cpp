@@ -170,3 +170,9 @@ extern "C" void hs_upsample2x(const float* src, float* dst, int n, int h, int w,
         }
       }
 }
+
+extern "C" void hs_mask_dilate(const uint8_t* src, float* dst, int T, int H, int W, int iterations) {
+  for (long f = 0; f < T; ++f)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) dst[(f * H + y) * W + x] = pp_mask_dilate_pixel(src + f * H * W, H, W, y, x, iterations);
+}

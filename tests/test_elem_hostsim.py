@@ -203,3 +203,17 @@ def test_upsample2x(hostsim):
         out = torch.empty(n, 2 * h, 2 * w, C)
         hostsim.hs_upsample2x(fp(xp), fp(out), n, h, w, C)
         assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-6, rtol=1e-6)
+
+
+def test_mask_dilate(hostsim):
+    import scipy.ndimage
+    gen = torch.Generator().manual_seed(12)
+    T, H, W = 3, 37, 53
+    m = (torch.rand(T, H, W, generator=gen) > 0.985).to(torch.uint8) * 255
+    m[0, 0, 0] = 255
+    m[1, H - 1, W - 1] = 7
+    for it in (0, 1, 4, 8):
+        ref = np.stack([scipy.ndimage.binary_dilation(m[i].numpy(), iterations=it) if it else m[i].numpy() > 0 for i in range(T)])
+        out = torch.empty(T, H, W)
+        hostsim.hs_mask_dilate(ctypes.c_void_p(m.data_ptr()), fp(out), T, H, W, it)
+        assert np.array_equal(out.numpy() > 0.5, ref), it

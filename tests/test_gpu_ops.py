@@ -295,3 +295,15 @@ def test_u8_and_composite():
             ref[i] = ref[i].astype(np.uint8)
         ops.composite_blend(pred.to(DEV), masks.to(DEV), u8.to(DEV), comp, ids, first)
     assert np.array_equal(comp.cpu().numpy(), np.stack(ref, 0))
+
+
+def test_mask_dilate():
+    import scipy.ndimage
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(12)
+    T, H, W = 3, 240, 432
+    m = (torch.rand(T, H, W, generator=gen) > 0.999).to(torch.uint8) * 255
+    for it in (0, 4):
+        ref = np.stack([scipy.ndimage.binary_dilation(m[i].numpy(), iterations=it) if it else m[i].numpy() > 0 for i in range(T)])
+        out = ops.mask_dilate(m.to(DEV), it).cpu()[:, 0].numpy()
+        assert np.array_equal(out > 0.5, ref) and set(np.unique(out)) <= {0.0, 1.0}
