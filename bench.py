@@ -264,6 +264,8 @@ def run_ours(args, wl):
     out_host = torch.empty_like(u8_host).pin_memory()
     pipe = ProPainterPipeline(device=dev)
     cfg = InferenceConfig(raft_iter=wl["raft_iter"])
+    if args.windows_in_flight:
+        cfg.windows_in_flight = args.windows_in_flight
     u8_dev, fm_dev, md_dev = u8_host.to(dev), fm_host.to(dev), md_host.to(dev)
     flush = torch.empty(64 * 1024 * 1024, device=dev)          # 256 MiB > 126 MB L2
 
@@ -347,6 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--windows-in-flight", type=int, default=0, help="override InferenceConfig.windows_in_flight")
     ap.add_argument("--shard", action="store_true", help="N>1: cooperate on ONE clip (strong scaling) instead of one clip per rank")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

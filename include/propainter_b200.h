@@ -63,10 +63,10 @@ int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int ld_prop, c
  * model/recurrent_flow_completion.py:31-44 after the conv_offset stack (torchvision.ops.deform_conv2d,
  * 3x3/s1/p1, 16 deform groups).  x pixel-major [H*W][ld_x] (Cin), o = raw conv_offset output
  * [H*W][ld_o>=432], flow [H*W][2] or NULL, w_packed [9*Cin][128] (row = tap*Cin + c), out [H*W][ld_out]. */
-size_t pp_deform_align_workspace_bytes(int H, int W);   /* split-K partial sums for small maps; may be 0 */
-int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
+size_t pp_deform_align_workspace_bytes(int H, int W);   /* decoded tap records + split-K partial sums */
+int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
                     const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin, int Cout,
-                    void* workspace, size_t ws_bytes, cudaStream_t stream);
+                    void* workspace, size_t ws_bytes, cudaStream_t stream);   /* o_bias: bias of conv_offset.6 if not yet added, else NULL */
 
 /* ---- generator glue ------------------------------------------------------------------------- */
 /* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar

@@ -109,34 +109,57 @@ extern "C" int pp_corr_build(const float* fmap, int D, const int* idx1, const in
 // LDS.128 of B feeds four MMAs and the epilogue stores float4.
 #define DA_LDA 40
 #define DA_LDB 132
-struct DAGather { float4 s0, s1; };
-__device__ __forceinline__ DAGather da_gather(const float* __restrict__ x, int ld_x, const float* __restrict__ op,
-                                              const float* __restrict__ fp, float max_res, int H, int W, int cpg, int k,
-                                              int c, int y, int xx, bool valid) {
-  DAGather r;
-  r.s0 = make_float4(0.f, 0.f, 0.f, 0.f); r.s1 = r.s0;
-  if (!valid) return r;
-  const PPDTap tp = pp_deform_tap(op, fp, max_res, c / cpg, k, y, xx);
-  const PPDW d = pp_deform_weights(tp, H, W);
-  const float* p = x + ((long)d.y0 * W + d.x0) * ld_x + c;
-#define PP_DACC(ptr, wt)                                                                         \
-  if ((wt) != 0.f) { const float4 u = *reinterpret_cast<const float4*>(ptr);                    \
-    const float4 v = *reinterpret_cast<const float4*>((ptr) + 4);                               \
-    r.s0.x += u.x * (wt); r.s0.y += u.y * (wt); r.s0.z += u.z * (wt); r.s0.w += u.w * (wt);     \
-    r.s1.x += v.x * (wt); r.s1.y += v.y * (wt); r.s1.z += v.z * (wt); r.s1.w += v.w * (wt); }
-  PP_DACC(p, d.w00)
-  PP_DACC(p + ld_x, d.w01)
-  PP_DACC(p + (long)W * ld_x, d.w10)
-  PP_DACC(p + (long)W * ld_x + ld_x, d.w11)
-#undef PP_DACC
-  return r;
+
+// pre-pass: decode the offset-net output once per (pixel, tap, group) -> (py, px, modulation), so the GEMM kernel's
+// inner loop has no transcendental math and reads its sampling positions as one aligned 16-byte load.
+// propainter.py:58-65 / recurrent_flow_completion.py:34-40; `obias` = bias of conv_offset.6 (folded in here).
+__global__ void __launch_bounds__(256) k_deform_taps(const float* __restrict__ o, int ld_o, const float* __restrict__ obias,
+    const float* __restrict__ flow, float max_res, float4* __restrict__ taps, int H, int W) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // (pix*9 + k)*16 + g
+  if (i >= (long)H * W * 144) return;
+  const int g = (int)(i & 15); const long r = i >> 4; const int k = (int)(r % 9); const long pix = r / 9;
+  const int y = (int)(pix / W), x = (int)(pix - (long)y * W);
+  const float* op = o + pix * ld_o;
+  float oy = op[g * 18 + 2 * k], ox = op[g * 18 + 2 * k + 1], ml = op[288 + g * 9 + k];
+  if (obias) { oy += obias[g * 18 + 2 * k]; ox += obias[g * 18 + 2 * k + 1]; ml += obias[288 + g * 9 + k]; }
+  oy = max_res * tanhf(oy); ox = max_res * tanhf(ox);
+  if (flow) { oy += flow[2 * pix + 1]; ox += flow[2 * pix]; }
+  taps[i] = make_float4((float)(y - 1 + k / 3) + oy, (float)(x - 1 + k % 3) + ox, 1.0f / (1.0f + expf(-ml)), 0.f);
 }
 
-__global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float* __restrict__ o,
-    int ld_o, const float* __restrict__ flow, float max_res, const float* __restrict__ Wp,
-    const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin, float* __restrict__ part) {
+struct DARaw { float4 u[4], v[4]; float w[4]; };
+// issue the 8 corner loads of (tap position tp, 8 channels from c); corners with zero weight read a safe address
+__device__ __forceinline__ void da_issue(const float* __restrict__ x, int ld_x, const float4 tp, int H, int W, int c, bool valid,
+                                         DARaw& r) {
+  PPDTap t; t.py = tp.x; t.px = tp.y; t.m = valid ? tp.z : 0.f;
+  const PPDW d = pp_deform_weights(t, H, W);
+  r.w[0] = d.w00; r.w[1] = d.w01; r.w[2] = d.w10; r.w[3] = d.w11;
+  const float* p = x + ((long)d.y0 * W + d.x0) * ld_x + c;
+  const float* q[4] = {p, p + ld_x, p + (long)W * ld_x, p + (long)W * ld_x + ld_x};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* a = r.w[j] != 0.f ? q[j] : x + c;                // never dereference an out-of-image corner
+    r.u[j] = *reinterpret_cast<const float4*>(a);
+    r.v[j] = *reinterpret_cast<const float4*>(a + 4);
+  }
+}
+__device__ __forceinline__ void da_combine(const DARaw& r, float4& s0, float4& s1) {
+  s0 = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float w = r.w[j];
+    s0.x += r.u[j].x * w; s0.y += r.u[j].y * w; s0.z += r.u[j].z * w; s0.w += r.u[j].w * w;
+    s1.x += r.v[j].x * w; s1.y += r.v[j].y * w; s1.z += r.v[j].z * w; s1.w += r.v[j].w * w;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float4* __restrict__ taps,
+    const float* __restrict__ Wp, const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin,
+    float* __restrict__ part) {
   // gridDim.y > 1: split-K over the 9*Cin/32 K-steps -- CTA row y accumulates its share into part[y][pix][128]
   // (reduced + biased by k_deform_reduce); a 6480- or 1620-pixel map alone gives only 203 / 51 CTAs.
+  // Software pipeline per K-step `it`: the tap record of step it+2 and the 8 corner loads of step it+1 are issued
+  // BEFORE the MMAs of step it and consumed after them, and the weight slab of it+1 arrives by cp.async meanwhile.
   __shared__ __align__(16) float As[2][32][DA_LDA];
   __shared__ __align__(16) float Bs[2][32][DA_LDB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -145,11 +168,9 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
   const long npix = (long)H * W;
   const long pix = (long)blockIdx.x * 32 + px_l;
   const bool valid = pix < npix;
-  const int y = valid ? (int)(pix / W) : 0, xx = valid ? (int)(pix - (long)y * W) : 0;
+  const long pixc = valid ? pix : 0;
   const int cpg = Cin / 16, cblocks = Cin / 32, nit_all = 9 * cblocks;
   const int it0 = (int)((long)nit_all * blockIdx.y / gridDim.y), it1 = (int)((long)nit_all * (blockIdx.y + 1) / gridDim.y);
-  const float* op = o + (valid ? pix : 0) * ld_o;
-  const float* fp = flow ? flow + 2 * (valid ? pix : 0) : nullptr;
   float acc[8][4];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
@@ -164,27 +185,31 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
     }
     pp_cp_async_commit();
   };
-  auto store_a = [&](const DAGather& r, int buf) {
-    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8]) = r.s0;
-    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8 + 4]) = r.s1;
+  auto chan = [&](int it) { const int k = it / cblocks; return (it - k * cblocks) * 32 + cseg * 8; };
+  auto tap_of = [&](int it) { const int k = it / cblocks; return taps[(pixc * 9 + k) * 16 + chan(it) / cpg]; };
+  auto store_a = [&](const DARaw& r, int buf) {
+    float4 s0, s1;
+    da_combine(r, s0, s1);
+    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8]) = s0;
+    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8 + 4]) = s1;
   };
 
+  DARaw raw;
   load_b(it0, 0);
-  {
-    const int k0 = it0 / cblocks;
-    store_a(da_gather(x, ld_x, op, fp, max_res, H, W, cpg, k0, (it0 - k0 * cblocks) * 32 + cseg * 8, y, xx, valid), 0);
-  }
+  da_issue(x, ld_x, tap_of(it0), H, W, chan(it0), valid, raw);
+  float4 tp_next = it0 + 1 < it1 ? tap_of(it0 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  store_a(raw, 0);
   pp_cp_async_wait<0>();
   __syncthreads();
 
   for (int it = it0; it < it1; ++it) {
     const int cur = (it - it0) & 1, nxt = cur ^ 1;
     const bool more = it + 1 < it1;
-    DAGather nx;
+    float4 tp_next2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (more) {
       load_b(it + 1, nxt);
-      const int k1 = (it + 1) / cblocks, c1 = ((it + 1) - k1 * cblocks) * 32 + cseg * 8;
-      nx = da_gather(x, ld_x, op, fp, max_res, H, W, cpg, k1, c1, y, xx, valid);
+      if (it + 2 < it1) tp_next2 = tap_of(it + 2);
+      da_issue(x, ld_x, tp_next, H, W, chan(it + 1), valid, raw);
     }
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -205,9 +230,10 @@ __global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ 
       }
     }
     if (more) {
-      store_a(nx, nxt);
+      store_a(raw, nxt);
       pp_cp_async_wait<0>();
     }
+    tp_next = tp_next2;
     __syncthreads();
   }
   // epilogue: tile 4q+j, C-fragment column 2t+c  <->  physical column wn*64 + 32q + 4(2t+c) + j
@@ -254,24 +280,27 @@ static int da_splits(long npix) {
 extern "C" size_t pp_deform_align_workspace_bytes(int H, int W) {
   const long npix = (long)H * W;
   const int s = da_splits(npix);
-  return s > 1 ? (size_t)s * npix * 128 * sizeof(float) : 0;
+  return (size_t)npix * 144 * sizeof(float4) + (s > 1 ? (size_t)s * npix * 128 * sizeof(float) : 0);   // tap records + split-K partials
 }
 
 // replaces DeformableAlignment.forward / SecondOrderDeformableAlignment.forward after the offset-net
-// convs (model/propainter.py:57-69, model/recurrent_flow_completion.py:31-44 -> torchvision deform_conv2d)
-extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* flow, float max_res,
-                               const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin,
-                               int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+// convs (model/propainter.py:57-69, model/recurrent_flow_completion.py:31-44 -> torchvision deform_conv2d).
+// `o` is the raw output of conv_offset.6; pass its bias as `o_bias` if it has not been added yet (else NULL).
+extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
+                               float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int H, int W,
+                               int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   if (Cout != 128 || Cin % 32 || (Cin / 16) % 8) return PP_ERR_SHAPE;
-  if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
+  if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)x & 15)) return PP_ERR_ALIGN;
   const long npix = (long)H * W;
   const int splits = da_splits(npix);
-  if (ws_bytes < pp_deform_align_workspace_bytes(H, W) || (splits > 1 && ((uintptr_t)workspace & 15))) return PP_ERR_WORKSPACE;
+  if (ws_bytes < pp_deform_align_workspace_bytes(H, W) || ((uintptr_t)workspace & 15)) return PP_ERR_WORKSPACE;
+  float4* taps = (float4*)workspace;
+  float* part = (float*)(taps + npix * 144);
+  k_deform_taps<<<(int)((npix * 144 + 255) / 256), 256, 0, stream>>>(o, ld_o, o_bias, flow, max_res, taps, H, W);
   dim3 grid((unsigned)((npix + 31) / 32), splits);
-  k_deform_align<<<grid, 128, 0, stream>>>(x, ld_x, o, ld_o, flow, max_res, w_packed, bias, out, ld_out, H, W, Cin,
-                                           (float*)workspace);
+  k_deform_align<<<grid, 128, 0, stream>>>(x, ld_x, taps, w_packed, bias, out, ld_out, H, W, Cin, part);
   if (splits > 1)
-    k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>((const float*)workspace, bias, out, ld_out, npix, splits);
+    k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>(part, bias, out, ld_out, npix, splits);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -26,7 +26,7 @@ class InferenceConfig:
     # frames per RAFT call.  None = as many as an 8 GB correlation pyramid allows (never fewer than the reference's
     # 12/8/4/2, inference_propainter.py:302-309).  Frame pairs are independent, so this only changes batching.
     raft_clip_frames: int = None
-    windows_in_flight: int = 2      # generator windows computed concurrently on separate streams (compositing stays ordered)
+    windows_in_flight: int = 3      # generator windows computed concurrently on separate streams (compositing stays ordered)
 
 
 def get_ref_index(mid_neighbor_id, neighbor_ids, length, ref_stride=10, ref_num=-1):

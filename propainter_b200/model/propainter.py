@@ -116,8 +116,9 @@ class InpaintGenerator(ParamNet):
                     o = conv(as_nchw(cond), self._wb(p + "0", 2 * C + 8), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._wb(p + "2"), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._wb(p + "4"), 1, 1, act="leaky", slope=0.1)
-                    o = as_pm(conv(o, self._wb(p + "6"), 1, 1))
-                    ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C])
+                    w6, b6 = self._wb(p + "6")
+                    o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
+                    ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C], o_bias=b6)
                 y = conv(conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2),
                          self._wb(f"{fp}backbone.{name}.2"), 1, 1)
                 torch.add(bb[0, :, :, C:2 * C], as_pm(y)[0], out=dst[idx])

@@ -94,9 +94,10 @@ class RecurrentFlowCompleteNet(ParamNet):
                     o = conv(as_nchw(buf), self._offset_w0(name), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1, act="leaky", slope=0.1)
-                    o = as_pm(conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.6"), 1, 1))
+                    w6, b6 = self._w2d(f"{fp}deform_align.{name}.conv_offset.6")
+                    o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
                     aligned = torch.empty(1, h, w, c, device=dev)
-                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, aligned[0])
+                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, aligned[0], o_bias=b6)
                     prop = aligned
                 parts = [cur] + ([results["backward_"][idx:idx + 1]] if di == 1 else []) + [prop]
                 f = as_nchw(torch.cat(parts, -1))

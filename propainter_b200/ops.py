@@ -127,8 +127,9 @@ def prop_cond(cur, prop, fprop, fcheck, mcur, cond, bb, first):
     _count(1)
 
 
-def deform_align(x, o, flow, max_res, w_packed, bias, out):
-    """x [H,W,Cin] view, o [H,W,>=432] view, flow [H,W,2]|None, out [H,W,128] view (all pixel-major)."""
+def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
+    """x [H,W,Cin] view, o [H,W,>=432] view (raw conv_offset.6 output; its bias may be passed as o_bias instead of being
+    pre-added), flow [H,W,2]|None, out [H,W,128] view (all pixel-major)."""
     H, W, Cin = x.shape
     xp, ldx = _pm(x)
     op, ldo = _pm(o)
@@ -136,9 +137,9 @@ def deform_align(x, o, flow, max_res, w_packed, bias, out):
     L = _lib.lib()
     ws_bytes = L.pp_deform_align_workspace_bytes(H, W)
     ws = torch.empty(max(ws_bytes // 4, 4), device=x.device, dtype=torch.float32)
-    check(L.pp_deform_align(xp, ldx, op, ldo, _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp, ldout, H, W,
-                            Cin, out.shape[-1], _p(ws), ws_bytes, _stream()), "pp_deform_align")
-    _count(2 if ws_bytes else 1)
+    check(L.pp_deform_align(xp, ldx, op, ldo, _p(o_bias), _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp, ldout,
+                            H, W, Cin, out.shape[-1], _p(ws), ws_bytes, _stream()), "pp_deform_align")
+    _count(3 if ws_bytes > H * W * 144 * 16 else 2)
     return out
 
 

@@ -68,8 +68,10 @@ def install(monkeypatch, hostsim):
         assert t.dtype == torch.float32 and t.stride(-1) == 1
         return ctypes.cast(t.data_ptr(), FP)
 
-    def deform_align(x, o, flow, max_res, w_packed, bias, out):
+    def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
         H, W, Cin = x.shape
+        if o_bias is not None:
+            o = (o + o_bias).contiguous()
         cols = torch.empty(H * W, 9 * Cin)
         hostsim.hs_deform_cols(_fp_view(x), x.stride(-2), _fp_view(o), o.stride(-2), _fp(flow) if flow is not None else None,
                                ctypes.c_float(max_res), _fp(cols), H, W, Cin)
