@@ -272,14 +272,21 @@ __global__ void __launch_bounds__(256) k_deform_reduce(const float* __restrict__
   *reinterpret_cast<float4*>(out + pix * ld_out + n) = s;
 }
 
-static int da_splits(long npix) {
-  const long ctas = (npix + 31) / 32;
-  if (ctas >= 4 * PP_NUM_SMS) return 1;
-  return ctas * 3 >= 3 * PP_NUM_SMS ? 3 : 9;
+// split-K factor: the kernel is latency-bound, so what matters is (waves of resident CTAs) x (K-steps per CTA + prologue).
+// 4 CTAs fit per SM (126 registers x 128 threads, 44 KB shared memory); ties go to the smaller factor (less reduce traffic).
+static int da_splits(long npix, int nit) {
+  const long ctas = (npix + 31) / 32, slots = 4L * PP_NUM_SMS;
+  int best = 1; long best_cost = -1;
+  for (int s = 1; s <= 9; ++s) {
+    const long waves = (ctas * s + slots - 1) / slots, steps = (nit + s - 1) / s;
+    const long cost = waves * (steps + 2) * 16 + (s > 1 ? s : 0);
+    if (best_cost < 0 || cost < best_cost) { best = s; best_cost = cost; }
+  }
+  return best;
 }
 extern "C" size_t pp_deform_align_workspace_bytes(int H, int W) {
   const long npix = (long)H * W;
-  const int s = da_splits(npix);
+  const int s = da_splits(npix, 36) > da_splits(npix, 72) ? da_splits(npix, 36) : da_splits(npix, 72);
   return (size_t)npix * 144 * sizeof(float4) + (s > 1 ? (size_t)s * npix * 128 * sizeof(float) : 0);   // tap records + split-K partials
 }
 
@@ -292,7 +299,7 @@ extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_
   if (Cout != 128 || Cin % 32 || (Cin / 16) % 8) return PP_ERR_SHAPE;
   if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)x & 15)) return PP_ERR_ALIGN;
   const long npix = (long)H * W;
-  const int splits = da_splits(npix);
+  const int splits = da_splits(npix, 9 * (Cin / 32));
   if (ws_bytes < pp_deform_align_workspace_bytes(H, W) || ((uintptr_t)workspace & 15)) return PP_ERR_WORKSPACE;
   float4* taps = (float4*)workspace;
   float* part = (float*)(taps + npix * 144);

@@ -139,7 +139,7 @@ def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
     ws = torch.empty(max(ws_bytes // 4, 4), device=x.device, dtype=torch.float32)
     check(L.pp_deform_align(xp, ldx, op, ldo, _p(o_bias), _p(flow), float(max_res), _p(_dense(w_packed)), _p(bias), outp, ldout,
                             H, W, Cin, out.shape[-1], _p(ws), ws_bytes, _stream()), "pp_deform_align")
-    _count(3 if ws_bytes > H * W * 144 * 16 else 2)
+    _count(3)                                                    # tap pre-pass, GEMM, (split-K reduce)
     return out
 
 

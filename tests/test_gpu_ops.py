@@ -173,6 +173,12 @@ def test_deform_align():
         scale = ref.abs().max().item()
         assert (got - ref).abs().max().item() < 2e-3 * scale, ((got - ref).abs().max().item(), scale)
         assert (out[..., :128] == 0).all() and (out[..., 256:] == 0).all()
+        # same result when the offset-net bias is folded into the tap pre-pass instead of being pre-added
+        ob = torch.randn(432, generator=gen) * 0.3
+        out2 = torch.zeros(H, W, 128, device=DEV)
+        ops.deform_align(xbuf[..., :Cin], (o[0].permute(1, 2, 0) - ob).contiguous().to(DEV), fl, max_res,
+                         ops.pack_deform_weight(wgt).to(DEV), bias.to(DEV), out2, o_bias=ob.to(DEV))
+        assert (out2.cpu().permute(2, 0, 1) - ref).abs().max().item() < 2e-3 * scale
 
 
 def test_sparse_window_attention():
