@@ -133,7 +133,10 @@ class ParamNet(nn.Module):
             for key in self._keys:
                 parts = key.split(".")
                 node = _descend(self, parts[:-1], create=False)
-                flat[key] = getattr(node, parts[-1])
+                t = getattr(node, parts[-1])
+                # .half() nets (reference inference_propainter.py:268-270, --fp16): storage may be fp16/bf16, the
+                # kernels compute in fp32, so the live view the forward code sees is widened once per dtype move.
+                flat[key] = t.float() if t.is_floating_point() and t.dtype != torch.float32 else t
             self._flat = flat
         return self._flat
 

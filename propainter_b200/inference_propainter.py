@@ -27,6 +27,10 @@ class InferenceConfig:
     # 12/8/4/2, inference_propainter.py:302-309).  Frame pairs are independent, so this only changes batching.
     raft_clip_frames: int = None
     windows_in_flight: int = 3      # generator windows computed concurrently on separate streams (compositing stays ordered)
+    # --fp16 (inference_propainter.py:211, :268-270, :323-330) halves the two nets and every tensor after RAFT.  The
+    # kernels here compute in fp32 whatever the storage dtype (a `.half()` net is widened once, fp16 inputs are widened at
+    # entry and results handed back in the caller's dtype), so the flag is accepted and changes nothing in the pipeline.
+    fp16: bool = False
 
 
 def get_ref_index(mid_neighbor_id, neighbor_ids, length, ref_stride=10, ref_num=-1):

@@ -61,7 +61,8 @@ class InpaintGenerator(ParamNet):
                                      interpolation == "nearest")
             fr.append(f)
             mk.append(m)
-        return torch.stack(fr, 0), torch.stack(mk, 0)
+        dt = masked_frames.dtype                                   # fp16 callers (--fp16) get fp16 back; math is fp32
+        return torch.stack(fr, 0).to(dt), torch.stack(mk, 0).to(dt)
 
     # ------------------------------------------------------------------ conv trunk
     def _encoder(self, x):
@@ -174,7 +175,7 @@ class InpaintGenerator(ParamNet):
             enc = self.encode(masked_frames[bi], masks_in[bi], masks_updated[bi])
             res.append(self.forward_features(enc, (completed_flows[0][bi], completed_flows[1][bi]), masks_in[bi],
                                              masks_updated[bi], lt, interpolation, t_dilation))
-        return torch.stack(res, 0).view(b, lt, 3, H, W)
+        return torch.stack(res, 0).view(b, lt, 3, H, W).to(masked_frames.dtype)
 
     def _forward_features(self, enc, flows_f, flows_b, mi, mu, lt, interpolation, t_dilation):
         """one window after the encoder; captured as one CUDA graph per shape signature."""

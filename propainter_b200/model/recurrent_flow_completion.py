@@ -116,7 +116,7 @@ class RecurrentFlowCompleteNet(ParamNet):
         b, t, _, h, w = masked_flows.shape
         outs = [self.graphs("rfc", self._forward_one, masked_flows[bi].contiguous().float(), masks[bi].contiguous().float())
                 for bi in range(b)]
-        return torch.stack(outs, 0).view(b, t, 2, h, w), None
+        return torch.stack(outs, 0).view(b, t, 2, h, w).to(masked_flows.dtype), None
 
     def _forward_one(self, flows, masks):
         """one clip: flows [t,2,h,w], masks [t,1,h,w] -> [t,2,h,w]; captured as a CUDA graph per shape."""
@@ -150,7 +150,8 @@ class RecurrentFlowCompleteNet(ParamNet):
                                xb[bi].contiguous().float(), mbf[bi].contiguous().float())
             pf.append(f)
             pb.append(g)
-        pf, pb = torch.stack(pf, 0).view(b, t, 2, h, w), torch.stack(pb, 0).view(b, t, 2, h, w)
+        dt = masked_flows_bi[0].dtype                              # fp16 storage in, fp16 out; the scan itself is fp32
+        pf, pb = torch.stack(pf, 0).view(b, t, 2, h, w).to(dt), torch.stack(pb, 0).view(b, t, 2, h, w).to(dt)
         return [pf, torch.flip(pb, dims=[1])], [None, None]
 
     def _forward_pair(self, xf, mf, xb, mb):

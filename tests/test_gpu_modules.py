@@ -101,6 +101,30 @@ def test_generator_matches_oracle(H, W, t, lt):
     assert out.shape == (1, lt, 3, H, W) and e < 2e-2
 
 
+def test_generator_half_storage():
+    """--fp16 call surface (inference_propainter.py:268-270, :323-330): `.half()` net + fp16 tensors.  Storage is fp16,
+    the kernels still compute in fp32, so the result must match the fp32 oracle run on the *rounded* weights/inputs to
+    fp16 output rounding."""
+    from propainter_b200.model.propainter import InpaintGenerator
+    H, W, t, lt = 128, 128, 5, 3
+    net = InpaintGenerator(seed=3).half().to(DEV)
+    gen = torch.Generator().manual_seed(1)
+    frames = (torch.rand(1, t, 3, H, W, generator=gen) * 2 - 1).half()
+    sm = lambda z: F.avg_pool2d(z.view(-1, 2, H, W), 9, 1, 4).view(z.shape)
+    flows = tuple(sm(torch.randn(1, lt - 1, 2, H, W, generator=gen) * 12).half() for _ in range(2))
+    masks = torch.zeros(1, t, 1, H, W)
+    masks[..., H // 4:H // 2, W // 3:2 * W // 3] = 1
+    masks = masks.half()
+    mf = frames * (1 - masks)
+    out = net(mf.to(DEV), (flows[0].to(DEV), flows[1].to(DEV)), masks.to(DEV), masks.to(DEV), lt)
+    assert out.dtype == torch.float16 and out.shape == (1, lt, 3, H, W)
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in cpu_sd(net).items()}
+    ref = generator_ref.generator_forward(sd, mf.float(), (flows[0].float(), flows[1].float()), masks.float(), masks.float(), lt)
+    e = rel_err(out.float().cpu(), ref)
+    print(f"generator fp16 storage: rel {e:.2e}")
+    assert e < 2e-2
+
+
 def test_img_propagation_api():
     from propainter_b200.model.propainter import InpaintGenerator
     net = InpaintGenerator(seed=3).to(DEV)

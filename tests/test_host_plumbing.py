@@ -78,3 +78,24 @@ def test_pipeline_plumbing(emu):
         assert rel_err(st["pred_flows"][k], rst["pred_flows"][k]) < 1e-3
     assert (st["updated_masks"] != rst["updated_masks"]).float().mean() < 2e-3
     assert ops_ref.psnr_u8(comp.numpy(), ref) > 50.0
+
+
+def test_half_storage_is_accepted(emu):
+    """`.half()` nets with fp16 tensors (reference --fp16, inference_propainter.py:268-270, :323-330): same call surface,
+    results come back in fp16 and agree with the fp32 run to fp16 rounding (the math itself stays fp32)."""
+    from propainter_b200.model.recurrent_flow_completion import RecurrentFlowCompleteNet
+    torch.manual_seed(0)
+    net = RecurrentFlowCompleteNet(None, seed=3)
+    flows = (torch.randn(1, 3, 2, 32, 32), torch.randn(1, 3, 2, 32, 32))
+    masks = (torch.rand(1, 4, 1, 32, 32) > 0.6).float()
+    ref, _ = net.forward_bidirect_flow(flows, masks)
+    sd32 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.half()
+    assert all(v.dtype == torch.float16 for k, v in net.state_dict().items() if v.is_floating_point())
+    out, _ = net.forward_bidirect_flow((flows[0].half(), flows[1].half()), masks.half())
+    assert out[0].dtype == torch.float16 and out[1].dtype == torch.float16
+    for a, b in zip(out, ref):
+        assert (a.float() - b).abs().max() < 2e-2 * (1 + b.abs().max())
+    comb = net.combine_flow((flows[0].half(), flows[1].half()), out, masks.half())
+    assert comb[0].dtype == torch.float16
+    net.float().load_state_dict(sd32, strict=True)
