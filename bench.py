@@ -329,6 +329,11 @@ def run_ours(args, wl):
                     "h2d_bytes_per_step": u8_host.numel() + 4 * (fm_host.numel() + md_host.numel()),
                     "d2h_bytes_per_step": out_host.numel()},
         }
+        from propainter_b200 import autotune
+        plans = {}
+        for k, v in autotune.choices().items():                    # which measured plan each step replays (stderr, not the line)
+            plans.setdefault(f"{k[0]}[{v}]", []).append(str(k[1:3]))
+        print("autotune plans:", {k: (len(v), v[:4]) for k, v in plans.items()}, file=sys.stderr)
         try:
             line["roofline"] = roofline_probe(torch, pipe, wl)
         except Exception as exc:                                   # never lose the headline line to the probe

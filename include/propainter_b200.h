@@ -105,18 +105,30 @@ int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, i
  * and r*net into the state slice of RX (ld_r). */
 int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet, int ld_r,
                 long npix, int C, cudaStream_t stream);
-/* net = (1-z)*net + z*tanh(q + bias), in place on the state slice of HX. */
-int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, long npix, int C,
+/* net = (1-z)*net + z*tanh(q + bias), in place on the state slice of HX; net_copy (nullable, dense [npix][C]) also
+ * receives the new state (input of the flow / mask heads, RAFT/update.py:133-136). */
+int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, float* net_copy, long npix, int C,
                   cudaStream_t stream);
-/* motion features: channels [0,126) of `mot` + the 2 flow channels -> the same 128-channel slot of d0 and d1. */
-int pp_raft_pack_motion(const float* mot, int ld_mot, const float* flow, float* d0, float* d1, int ld, long npix,
-                        cudaStream_t stream);
+/* motion features: channels [0,126) of `mot` + the 2 flow channels -> the same 128-channel slot of d0 and d1.
+ * bias != NULL: `mot` is the raw conv output and relu(mot + bias) (RAFT/update.py:96) is applied on the way. */
+int pp_raft_pack_motion(const float* mot, int ld_mot, const float* bias, const float* flow, float* d0, float* d1, int ld,
+                        long npix, cudaStream_t stream);
 
 /* ---- conv epilogues ------------------------------------------------------------------------- */
-/* In-place y = act(x + bias[c]) on a dense pixel-major tensor [n_pix][C]: replaces the bias add of
- * F.conv2d plus the ReLU / LeakyReLU / sigmoid / tanh that follows it at every conv of the three nets.
- * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh. */
-int pp_bias_act(float* x, const float* bias, long n_pix, int C, int act, float slope, cudaStream_t stream);
+/* out = post(act(x + bias[c]) + res) on pixel-major tensors [n_pix][C] with pixel strides ld_*: replaces the bias add of
+ * F.conv2d, the ReLU / LeakyReLU / sigmoid / tanh that follows it at every conv of the three nets, the residual add
+ * (+ ReLU) of RAFT/extractor.py:49-57, model/propainter.py:173-176, model/recurrent_flow_completion.py:108-110, and --
+ * through a strided `out` -- the torch.cat of RAFT/update.py:95.  bias / res nullable; out may alias x.
+ * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh; post_relu: final ReLU after the residual add. */
+int pp_bias_act(const float* x, int ld_x, const float* bias, const float* res, int ld_res, float* out, int ld_out, long n_pix,
+                int C, int act, float slope, int post_relu, cudaStream_t stream);
+
+/* nn.InstanceNorm2d(affine=False, eps) of the RAFT feature encoder (RAFT/extractor.py:18-21,125,168-192) on channels-last
+ * maps x [n][HW][C]: out = post(relu?((x - mean) * rstd) + res), statistics per (sample, channel), biased variance.
+ * res nullable (dense, same shape); out may alias x. */
+size_t pp_instance_norm_workspace_bytes(int n, long HW, int C);
+int pp_instance_norm(const float* x, const float* res, float* out, int n, long HW, int C, float eps, int relu, int post_relu,
+                     void* workspace, size_t ws_bytes, cudaStream_t stream);
 /* `deconv` up-sampling, F.interpolate(scale_factor=2, bilinear, align_corners=True)
  * (model/propainter.py:248-253, model/recurrent_flow_completion.py:141-146); pixel-major [n][h][w][C] -> [n][2h][2w][C]. */
 int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h, int w, int C, cudaStream_t stream);

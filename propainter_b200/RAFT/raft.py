@@ -63,13 +63,19 @@ class RAFT(ParamNet):
 
     # ------------------------------------------------------------------ encoders (extractor.py:168-192)
     def _encode(self, p, x):
+        """BasicEncoder.forward extractor.py:168-192.  fnet: conv -> InstanceNorm -> ReLU with the norm, the ReLU and the
+        block's `relu(x + y)` as one pp_instance_norm call on the raw conv output (the conv bias cancels under the
+        per-channel mean subtraction, so it is not even added).  cnet: eval BatchNorm folded into the conv; bias, ReLU
+        and the residual add + ReLU are one pp_bias_act pass."""
         inst = p == "fnet"
 
-        def cn(key, bn, t, stride=1, pad=1, relu=True):
-            if inst:                                            # conv -> InstanceNorm -> ReLU
-                y = F.instance_norm(conv(t, self._wb(key), stride, pad), eps=1e-5)
-                return F.relu_(y) if relu else y
-            return conv(t, self._wb(key, bn), stride, pad, act="relu" if relu else "none")    # BN folded
+        def cn(key, bn, t, stride=1, pad=1, relu=True, res=None):
+            if inst:
+                w, _ = self._wb(key)
+                y = as_pm(F.conv2d(t, w, None, stride=stride, padding=pad))
+                return as_nchw(ops.instance_norm(y, relu=relu, res=None if res is None else as_pm(res),
+                                                 post_relu=res is not None, out=y))
+            return conv(t, self._wb(key, bn), stride, pad, act="relu" if relu else "none", res=res, post_relu=res is not None)
 
         x = cn(p + ".conv1", p + ".norm1", x, 2, 3)
         for li, stride in ((1, 1), (2, 2), (3, 2)):
@@ -77,10 +83,9 @@ class RAFT(ParamNet):
                 q = f"{p}.layer{li}.{bi}"
                 s = stride if bi == 0 else 1
                 y = cn(q + ".conv1", q + ".norm1", x, s, 1)
-                y = cn(q + ".conv2", q + ".norm2", y, 1, 1)
                 if s != 1:
                     x = cn(q + ".downsample.0", q + ".norm3", x, s, 0, relu=False)
-                x = F.relu_(x + y)
+                x = cn(q + ".conv2", q + ".norm2", y, 1, 1, res=x)              # relu(x + relu(norm(conv2(y))))
         return conv(x, self._wb(p + ".conv2"))
 
     def encode_frames(self, frames):
@@ -114,22 +119,26 @@ class RAFT(ParamNet):
         HX[..., 128:256] = as_pm(inp)
         RX[..., 128:256] = HX[..., 128:256]
         netv, z = HX[..., :128], torch.empty(B, h, w, 128, device=dev)
+        netc = torch.empty(B, h, w, 128, device=dev)            # dense copy of the state for the flow / mask heads
+        mot_in = torch.empty(B, h, w, 256, device=dev)          # [cor(192) | flo(64)] without a torch.cat (update.py:95)
+        mw, mb = self._motion_out()
         for _ in range(iters):
             ops.corr_lookup(levels, c1, corr)
             flow_pm = c1 - c0
             flow = as_nchw(flow_pm)
             cor = conv(as_nchw(corr), self._wb(u + "encoder.convc1"), act="relu")
-            cor = conv(cor, self._wb(u + "encoder.convc2"), 1, 1, act="relu")
+            conv(cor, self._wb(u + "encoder.convc2"), 1, 1, act="relu", out=as_nchw(mot_in[..., :192]))
             flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
-            flo = conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu")
-            mot = conv(torch.cat([cor, flo], 1), self._motion_out(), 1, 1, act="relu")          # 126 real + 2 pad channels
-            ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 256:], RX[..., 256:])
+            conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu", out=as_nchw(mot_in[..., 192:]))
+            mot = F.conv2d(as_nchw(mot_in), mw, None, padding=1)                   # 126 real + 2 pad channels, raw
+            ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 256:], RX[..., 256:], bias=mb)   # + bias + ReLU (update.py:96)
             for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
                 gw, gb = self._gates(tag)
                 qw, qb = self._wb(u + f"gru.convq{tag}")
                 ops.gru_gate(as_pm(F.conv2d(as_nchw(HX), gw, None, padding=pad)), gb, netv, z, RX[..., :128])
-                ops.gru_update(as_pm(F.conv2d(as_nchw(RX), qw, None, padding=pad)), qb, z, netv)
-            net = as_nchw(netv.contiguous())
+                ops.gru_update(as_pm(F.conv2d(as_nchw(RX), qw, None, padding=pad)), qb, z, netv,
+                               net_copy=netc if tag == "2" else None)
+            net = as_nchw(netc)
             d = conv(conv(net, self._wb(u + "flow_head.conv1"), 1, 1, act="relu"), self._wb(u + "flow_head.conv2"), 1, 1)
             c1 = c1 + as_pm(d)
         flow_lr = c1 - c0

@@ -8,6 +8,9 @@ LINEAR_TF32     plain Linear layers of the transformer (q/k/v, proj, fc1, fc2 = 
 CUDNN_BENCHMARK let cuDNN autotune conv algorithms during graph warm-up.
 CUDA_GRAPHS     replay each stage as a captured CUDA graph per shape signature (propainter_b200/graphs.py).
 FUSED_EPILOGUE  conv bias + activation through pp_bias_act (one pass) instead of cuDNN's bias add_ + ATen activation.
+AUTOTUNE        time numerically equivalent plans of a step once per shape during warm-up and keep the faster
+                (propainter_b200/autotune.py): grouped conv vs per-group dense convs, conv + pp_bias_act vs cuDNN's fused
+                conv-bias-ReLU.
 """
 import contextlib
 
@@ -17,6 +20,7 @@ LINEAR_TF32 = True
 CUDNN_BENCHMARK = True
 CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
+AUTOTUNE = True
 
 
 @contextlib.contextmanager

@@ -313,16 +313,23 @@ extern "C" int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, in
 }
 
 // ================================================================ conv epilogue + x2 upsampling
-// y = act(x + bias[c]) in place on a pixel-major tensor: one pass instead of cuDNN's separate bias
-// add_ kernel followed by the activation kernel.  act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh.
-__global__ void __launch_bounds__(256) k_bias_act(float* __restrict__ x, const float* __restrict__ bias, long n4, int C,
-                                                  int act, float slope) {
+// out = post(act(x + bias[c]) + res) on pixel-major tensors with explicit pixel strides: one pass instead of cuDNN's
+// separate bias add_ kernel, the activation kernel, the residual add and (with a strided `out`) the torch.cat that
+// would place the result into a concat buffer.  act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh; bias / res may
+// be NULL; post_relu applies a final ReLU (residual blocks).  out may alias x.
+__global__ void __launch_bounds__(256) k_bias_act(const float* x, int ld_x, const float* __restrict__ bias, const float* res,
+                                                  int ld_res, float* out, int ld_out, long n_pix, int C, int act, float slope,
+                                                  int post_relu) {
+  const int c4n = C >> 2;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)((i * 4) % C);
-  float4 v = reinterpret_cast<float4*>(x)[i];
-  const float4 b = *reinterpret_cast<const float4*>(bias + c);
-  float r[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
+  if (i >= n_pix * c4n) return;
+  const long pix = i / c4n; const int c = (int)(i - pix * c4n) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + pix * ld_x + c);
+  float r[4] = {v.x, v.y, v.z, v.w};
+  if (bias != nullptr) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + c);
+    r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float t = r[k];
@@ -332,13 +339,123 @@ __global__ void __launch_bounds__(256) k_bias_act(float* __restrict__ x, const f
     else if (act == 4) t = tanhf(t);
     r[k] = t;
   }
-  reinterpret_cast<float4*>(x)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  if (res != nullptr) {
+    const float4 q = *reinterpret_cast<const float4*>(res + pix * ld_res + c);
+    r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+  }
+  if (post_relu) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+  }
+  *reinterpret_cast<float4*>(out + pix * ld_out + c) = make_float4(r[0], r[1], r[2], r[3]);
 }
-// replaces the bias add of F.conv2d plus the following ReLU / LeakyReLU / sigmoid / tanh call
-extern "C" int pp_bias_act(float* x, const float* bias, long n_pix, int C, int act, float slope, cudaStream_t stream) {
-  if (C % 4 || ((uintptr_t)x & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
-  const long n4 = n_pix * C / 4;
-  k_bias_act<<<pp_blocks(n4, 256), 256, 0, stream>>>(x, bias, n4, C, act, slope);
+// replaces the bias add of F.conv2d, the following ReLU / LeakyReLU / sigmoid / tanh call, the residual `x + y`
+// (+ ReLU) of the encoder blocks / propagation backbones, and the torch.cat into a concat buffer
+extern "C" int pp_bias_act(const float* x, int ld_x, const float* bias, const float* res, int ld_res, float* out, int ld_out,
+                           long n_pix, int C, int act, float slope, int post_relu, cudaStream_t stream) {
+  if (C % 4 || ld_x % 4 || ld_out % 4 || (res && ld_res % 4)) return PP_ERR_ALIGN;
+  if (((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)res & 15)) return PP_ERR_ALIGN;
+  if (ld_x < C || ld_out < C || (res && ld_res < C) || act < 0 || act > 4) return PP_ERR_SHAPE;
+  if (n_pix <= 0) return PP_OK;
+  k_bias_act<<<pp_blocks(n_pix * (C / 4), 256), 256, 0, stream>>>(x, ld_x, bias, res, ld_res, out, ld_out, n_pix, C, act, slope,
+                                                                post_relu);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ================================================================ InstanceNorm (RAFT feature encoder)
+// RAFT/extractor.py:18-21,125 (nn.InstanceNorm2d, affine=False, eps 1e-5) on channels-last maps [n][HW][C]:
+// per (sample, channel) biased mean / variance over HW.  Pass 1 writes per-chunk partial sums, pass 2 folds them
+// (in double) and applies (x-mean)*rstd, the ReLU that always follows, and optionally the block's residual add + ReLU.
+// 3 passes over the map (2 reads, 1 write) instead of F.instance_norm's NHWC->NCHW copy, batch_norm and copy back.
+static int pp_in_splits(int n, long HW) {
+  int s = (592 + n - 1) / n;                      // ~4 CTAs per SM over the whole batch
+  if (s > 64) s = 64;
+  if ((long)s * 16 > HW) s = (int)((HW + 15) / 16);
+  return s < 1 ? 1 : s;
+}
+__global__ void __launch_bounds__(256) k_inorm_stats(const float* __restrict__ x, long HW, int C, int chunk, int S,
+                                                     float* __restrict__ part) {
+  __shared__ float4 sa[256], sb[256];
+  const int c4n = C >> 2, R = 256 / c4n;
+  const int q = threadIdx.x % c4n, r = threadIdx.x / c4n;
+  const long n = blockIdx.y; const int s = blockIdx.x;
+  const long r0 = (long)s * chunk; const long r1 = r0 + chunk < HW ? r0 + chunk : HW;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (r < R)
+    for (long row = r0 + r; row < r1; row += R) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (n * HW + row) * C + 4 * q);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      b.x += v.x * v.x; b.y += v.y * v.y; b.z += v.z * v.z; b.w += v.w * v.w;
+    }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  if (r == 0) {
+    for (int j = 1; j < R; ++j) {
+      const float4 u = sa[j * c4n + q], w = sb[j * c4n + q];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+    }
+    float* dst = part + ((n * S + s) * 2) * C + 4 * q;
+    *reinterpret_cast<float4*>(dst) = a;
+    *reinterpret_cast<float4*>(dst + C) = b;
+  }
+}
+__global__ void __launch_bounds__(256) k_inorm_apply(const float* x, const float* __restrict__ part, int S, const float* res,
+                                                     float* out, long HW, int C, int chunk, float eps, int relu, int post_relu) {
+  __shared__ float s_mean[512], s_rstd[512];
+  const long n = blockIdx.y; const int s = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double su = 0.0, sq = 0.0;
+    for (int j = 0; j < S; ++j) {
+      su += (double)part[((n * S + j) * 2) * C + c];
+      sq += (double)part[((n * S + j) * 2 + 1) * C + c];
+    }
+    const double mean = su / (double)HW;
+    double var = sq / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[c] = (float)mean;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int c4n = C >> 2, R = 256 / c4n;
+  const int q = threadIdx.x % c4n, r = threadIdx.x / c4n;
+  if (r >= R) return;
+  const float4 m = *reinterpret_cast<const float4*>(s_mean + 4 * q), k = *reinterpret_cast<const float4*>(s_rstd + 4 * q);
+  const long r0 = (long)s * chunk; const long r1 = r0 + chunk < HW ? r0 + chunk : HW;
+  for (long row = r0 + r; row < r1; row += R) {
+    const long off = (n * HW + row) * C + 4 * q;
+    const float4 v = *reinterpret_cast<const float4*>(x + off);
+    float y[4] = {(v.x - m.x) * k.x, (v.y - m.y) * k.y, (v.z - m.z) * k.z, (v.w - m.w) * k.w};
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+    }
+    if (res != nullptr) {
+      const float4 t = *reinterpret_cast<const float4*>(res + off);
+      y[0] += t.x; y[1] += t.y; y[2] += t.z; y[3] += t.w;
+    }
+    if (post_relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+    }
+    *reinterpret_cast<float4*>(out + off) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+extern "C" size_t pp_instance_norm_workspace_bytes(int n, long HW, int C) {
+  return (size_t)n * pp_in_splits(n, HW) * 2 * C * sizeof(float);
+}
+// replaces F.instance_norm (+ F.relu, + the residual `relu(x + y)` of ResidualBlock.forward extractor.py:49-57)
+extern "C" int pp_instance_norm(const float* x, const float* res, float* out, int n, long HW, int C, float eps, int relu,
+                                int post_relu, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (C % 4 || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)res & 15) || ((uintptr_t)workspace & 15)) return PP_ERR_ALIGN;
+  if (C < 4 || C > 512 || n < 1 || n > 65535 || HW < 1) return PP_ERR_SHAPE;
+  if (ws_bytes < pp_instance_norm_workspace_bytes(n, HW, C)) return PP_ERR_WORKSPACE;
+  const int S = pp_in_splits(n, HW);
+  const int chunk = (int)((HW + S - 1) / S);
+  float* part = (float*)workspace;
+  k_inorm_stats<<<dim3(S, n), 256, 0, stream>>>(x, HW, C, chunk, S, part);
+  k_inorm_apply<<<dim3(S, n), 256, 0, stream>>>(x, part, S, res, out, HW, C, chunk, eps, relu, post_relu);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -394,7 +511,7 @@ __global__ void __launch_bounds__(256) k_gru_gate(const float* __restrict__ zr, 
   *reinterpret_cast<float4*>(rnet + pix * ld_r + c) = ro;
 }
 __global__ void __launch_bounds__(256) k_gru_update(const float* __restrict__ q, const float* __restrict__ bias,
-    const float* __restrict__ z, float* __restrict__ net, int ld_net, long npix, int C) {
+    const float* __restrict__ z, float* __restrict__ net, int ld_net, float* __restrict__ net_copy, long npix, int C) {
   const int c4n = C >> 2;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * c4n) return;
@@ -405,6 +522,7 @@ __global__ void __launch_bounds__(256) k_gru_update(const float* __restrict__ q,
   h.x = (1.0f - zv.x) * h.x + zv.x * tanhf(qv.x + b.x); h.y = (1.0f - zv.y) * h.y + zv.y * tanhf(qv.y + b.y);
   h.z = (1.0f - zv.z) * h.z + zv.z * tanhf(qv.z + b.z); h.w = (1.0f - zv.w) * h.w + zv.w * tanhf(qv.w + b.w);
   *reinterpret_cast<float4*>(net + pix * ld_net + c) = h;
+  if (net_copy != nullptr) *reinterpret_cast<float4*>(net_copy + pix * C + c) = h;   // dense copy for the flow / mask heads
 }
 // z = sigmoid(conv_z), r*h (update.py:47-49 / :54-56): zr = raw output of the fused z|r conv [npix][2C]
 extern "C" int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet,
@@ -414,29 +532,33 @@ extern "C" int pp_gru_gate(const float* zr, const float* bias, const float* net,
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
-// h = (1-z)*h + z*tanh(conv_q) in place (update.py:50-51 / :57-58)
-extern "C" int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, long npix, int C,
-                             cudaStream_t stream) {
-  if (C % 4 || ld_net % 4) return PP_ERR_ALIGN;
-  k_gru_update<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(q, bias, z, net, ld_net, npix, C);
+// h = (1-z)*h + z*tanh(conv_q) in place (update.py:50-51 / :57-58); net_copy (nullable) also receives h densely
+extern "C" int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, float* net_copy,
+                             long npix, int C, cudaStream_t stream) {
+  if (C % 4 || ld_net % 4 || ((uintptr_t)net_copy & 15)) return PP_ERR_ALIGN;
+  k_gru_update<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(q, bias, z, net, ld_net, net_copy, npix, C);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 // motion features [out(126) | flow(2)] (update.py:95-97) written into the same channel slot of two buffers
-__global__ void __launch_bounds__(256) k_raft_pack_motion(const float* __restrict__ mot, int ld_mot, const float* __restrict__ flow,
-    float* __restrict__ d0, float* __restrict__ d1, int ld, long npix) {
+__global__ void __launch_bounds__(256) k_raft_pack_motion(const float* __restrict__ mot, int ld_mot, const float* __restrict__ bias,
+    const float* __restrict__ flow, float* __restrict__ d0, float* __restrict__ d1, int ld, long npix) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // 32 float4 per pixel (128 channels)
   if (i >= npix * 32) return;
   const long pix = i >> 5; const int c = (int)(i & 31) * 4;
   float4 v = *reinterpret_cast<const float4*>(mot + pix * ld_mot + c);
+  if (bias != nullptr) {                                        // raw conv output: bias + ReLU of update.py:96 applied here
+    const float4 b = *reinterpret_cast<const float4*>(bias + c);
+    v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+  }
   if (c == 124) { v.z = flow[2 * pix]; v.w = flow[2 * pix + 1]; }
   *reinterpret_cast<float4*>(d0 + pix * ld + c) = v;
   *reinterpret_cast<float4*>(d1 + pix * ld + c) = v;
 }
-extern "C" int pp_raft_pack_motion(const float* mot, int ld_mot, const float* flow, float* d0, float* d1, int ld, long npix,
-                                   cudaStream_t stream) {
-  if (ld % 4 || ld_mot % 4) return PP_ERR_ALIGN;
-  k_raft_pack_motion<<<pp_blocks(npix * 32, 256), 256, 0, stream>>>(mot, ld_mot, flow, d0, d1, ld, npix);
+extern "C" int pp_raft_pack_motion(const float* mot, int ld_mot, const float* bias, const float* flow, float* d0, float* d1,
+                                   int ld, long npix, cudaStream_t stream) {
+  if (ld % 4 || ld_mot % 4 || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
+  k_raft_pack_motion<<<pp_blocks(npix * 32, 256), 256, 0, stream>>>(mot, ld_mot, bias, flow, d0, d1, ld, npix);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

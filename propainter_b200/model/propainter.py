@@ -8,7 +8,7 @@ discriminators (:378-532) are training-only and not part of the inference path.
 import torch
 import torch.nn.functional as F
 
-from .. import ops
+from .. import autotune, ops
 from .._params import ParamNet
 from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels, up2
 from ..schemas import generator_schema
@@ -38,6 +38,14 @@ class InpaintGenerator(ParamNet):
                 w = pad_in_channels(w, cin_pad)
             return cl(w), self.P[key + ".bias"].contiguous()
         return self.packed(f"wb:{key}:{cin_pad}", build)
+
+    def _wb_group(self, key, j, g):
+        """(weight, bias) of group j of a grouped conv, as a dense conv."""
+        def build():
+            w, b = self.P[key + ".weight"], self.P[key + ".bias"]
+            co = w.shape[0] // g
+            return cl(w[j * co:(j + 1) * co]), b[j * co:(j + 1) * co].contiguous()
+        return self.packed(f"wbg:{key}:{j}", build)
 
     def _dcn(self, name):
         def build():
@@ -76,9 +84,26 @@ class InpaintGenerator(ParamNet):
         n, h, w, _ = x0.shape
         out = conv(out, self._wb("encoder.layers.8"), 1, 1, **L)
         for i, g in ((10, 2), (12, 4), (14, 8), (16, 1)):
+            key = f"encoder.layers.{i}"
+
+            def grouped(x0, o, key=key, g=g):               # one grouped conv over the interleaved [x0_j | o_j] groups
+                mix = torch.cat([x0.view(n, h, w, g, -1), o.view(n, h, w, g, -1)], -1).view(n, h, w, -1)
+                return conv(as_nchw(mix), self._wb(key), 1, 1, 1, g, **L)
+
+            def per_group(x0, o, key=key, g=g):             # the same math as g dense convs (cuDNN's grouped kernels are
+                a, b = x0.shape[-1] // g, o.shape[-1] // g  # several times slower than its dense ones at these shapes)
+                co = self.P[key + ".weight"].shape[0] // g
+                res = torch.empty(n, h, w, g * co, device=x0.device)
+                for j in range(g):
+                    xin = torch.cat([x0[..., j * a:(j + 1) * a], o[..., j * b:(j + 1) * b]], -1)
+                    conv(as_nchw(xin), self._wb_group(key, j, g), 1, 1, out=as_nchw(res[..., j * co:(j + 1) * co]), **L)
+                return as_nchw(res)
+
             o = as_pm(out)
-            mix = torch.cat([x0.view(n, h, w, g, -1), o.view(n, h, w, g, -1)], -1).view(n, h, w, -1)   # group-wise skip
-            out = conv(as_nchw(mix), self._wb(f"encoder.layers.{i}"), 1, 1, 1, g, **L)
+            if g == 1:
+                out = grouped(x0, o)
+            else:
+                out = autotune.pick(("enc_group", i, tuple(x0.shape), tuple(o.shape)), (grouped, per_group), x0, o)
         return out
 
     def _decoder(self, x):
@@ -120,15 +145,15 @@ class InpaintGenerator(ParamNet):
                     w6, b6 = self._wb(p + "6")
                     o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
                     ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C], o_bias=b6)
-                y = conv(conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2),
-                         self._wb(f"{fp}backbone.{name}.2"), 1, 1)
-                torch.add(bb[0, :, :, C:2 * C], as_pm(y)[0], out=dst[idx])
+                y = conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2)
+                # feat(idx) = aligned + backbone(...) (:173-176): bias, residual add and placement in one epilogue pass
+                conv(y, self._wb(f"{fp}backbone.{name}.2"), 1, 1, res=as_nchw(bb[:, :, :, C:2 * C]), out=as_nchw(dst[idx:idx + 1]))
                 prev = dst[idx]
             outs[name] = dst
             src = dst                                            # forward scan consumes the backward features (:138)
         z = torch.cat([outs["backward_1"], outs["forward_1"], pmask, pmask.new_zeros(lt, h, w, 2)], -1)
-        z = conv(conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2), self._wb(fp + "fuse.2"), 1, 1)
-        return z + as_nchw(x)
+        z = conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2)
+        return conv(z, self._wb(fp + "fuse.2"), 1, 1, res=as_nchw(x))
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()

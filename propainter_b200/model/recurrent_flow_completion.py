@@ -84,30 +84,32 @@ class RecurrentFlowCompleteNet(ParamNet):
         for di, name in enumerate(("backward_", "forward_")):
             order = list(range(t))[::-1] if di == 0 else list(range(t))
             hist = torch.zeros(t + 2, h, w, c, device=dev)                   # slots 0,1 = zero states
+            # backbone input of every step, [cur | (backward feature) | aligned state] (:101-106), laid out once per scan:
+            # the step-independent parts are filled by one copy, each step's deform-align writes its own last slot
+            k = 2 + di
+            fall = torch.empty(t, h, w, k * c, device=dev)
+            fall[..., :c] = xs
+            if di == 1:
+                fall[..., c:2 * c] = results["backward_"]
+            fall[order[0], :, :, -c:] = 0                                     # step 0 propagates the zero state
             dw, db = self._dcn(name)
             for i, idx in enumerate(order):
-                cur = xs[idx:idx + 1]
-                prop = hist[i + 1:i + 2]                                      # state of step i-1 (zeros for i=0)
+                pslot = fall[idx:idx + 1, :, :, -c:]                          # [1,h,w,128] view, pixel stride k*128
                 if i > 0:
-                    n2 = hist[i:i + 1]                                        # state of step i-2 (zeros for i=1)
-                    buf = torch.cat([prop, n2, cur], -1)                      # [1,h,w,384] = deform input | cur
+                    # deform input | cur: [state(i-1) | state(i-2) | cur]
+                    buf = torch.cat([hist[i + 1:i + 2], hist[i:i + 1], xs[idx:idx + 1]], -1)
                     o = conv(as_nchw(buf), self._offset_w0(name), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1, act="leaky", slope=0.1)
                     o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1, act="leaky", slope=0.1)
                     w6, b6 = self._w2d(f"{fp}deform_align.{name}.conv_offset.6")
                     o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
-                    aligned = torch.empty(1, h, w, c, device=dev)
-                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, aligned[0], o_bias=b6)
-                    prop = aligned
-                parts = [cur] + ([results["backward_"][idx:idx + 1]] if di == 1 else []) + [prop]
-                f = as_nchw(torch.cat(parts, -1))
-                y = conv(conv(f, self._w2d(f"{fp}backbone.{name}.0"), 1, 1, act="leaky", slope=0.1),
-                         self._w2d(f"{fp}backbone.{name}.2"), 1, 1)
-                hist[i + 2] = prop[0] + as_pm(y)[0]
+                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, pslot[0], o_bias=b6)
+                y = conv(as_nchw(fall[idx:idx + 1]), self._w2d(f"{fp}backbone.{name}.0"), 1, 1, act="leaky", slope=0.1)
+                # state(i) = aligned + backbone(...) (:108-110): bias, residual add and placement in one epilogue pass
+                conv(y, self._w2d(f"{fp}backbone.{name}.2"), 1, 1, res=as_nchw(pslot), out=as_nchw(hist[i + 2:i + 3]))
             seq = hist[2:]
             results[name] = seq.flip(0) if di == 0 else seq
-        fused = conv(as_nchw(torch.cat([results["backward_"], results["forward_"]], -1)), self._w2d(fp + "fusion"))
-        return fused + x
+        return conv(as_nchw(torch.cat([results["backward_"], results["forward_"]], -1)), self._w2d(fp + "fusion"), res=x)
 
     # ------------------------------------------------------------------ API
     @torch.no_grad()

@@ -6,7 +6,7 @@ Convolutions / plain Linear layers stay library calls (cuDNN / cuBLAS through to
 import torch
 import torch.nn.functional as F
 
-from . import config, ops
+from . import autotune, config, ops
 
 
 def cl(w):
@@ -43,20 +43,42 @@ _TORCH_ACT = {
 }
 
 
-def conv(x, wb, stride=1, padding=0, dilation=1, groups=1, act="none", slope=0.0):
-    """conv2d + bias + activation.  The conv is cuDNN; bias + activation are one pass of pp_bias_act on the
-    channels-last result (cuDNN would launch a separate bias add_, ATen another kernel for the activation).
-    Outputs whose channel count is not a multiple of 4 (2/3/126-channel heads) keep the library epilogue."""
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv(x, wb, stride=1, padding=0, dilation=1, groups=1, act="none", slope=0.0, res=None, post_relu=False, out=None):
+    """conv2d + bias + activation (+ residual add, + final ReLU, + placement into a channel slice `out`).
+    The conv is cuDNN; everything after it is one pass of pp_bias_act over the channels-last result (cuDNN would launch
+    a separate bias add_, ATen one kernel each for the activation, the residual add and the torch.cat).  `res` / `out`
+    are NCHW-logical channels_last views.  Plain conv+bias+ReLU may instead run as cuDNN's fused conv-bias-ReLU when
+    that measures faster for the shape (autotune.pick).  Outputs whose channel count is not a multiple of 4
+    (2/3-channel heads) keep the library epilogue."""
     w, b = wb
-    if config.FUSED_EPILOGUE and w.shape[0] % 4 == 0:
-        y = F.conv2d(x, w, None, stride=stride, padding=padding, dilation=dilation, groups=groups)
-        ypm = y.permute(0, 2, 3, 1)
-        if ypm.is_contiguous():
-            ops.bias_act_(ypm, b, act, slope)
-            return y
-        return _TORCH_ACT[act](y.add_(b.view(1, -1, 1, 1)), slope)
-    y = F.conv2d(x, w, b, stride=stride, padding=padding, dilation=dilation, groups=groups)
-    return _TORCH_ACT[act](y, slope)
+    st, pd, dl = _pair(stride), _pair(padding), _pair(dilation)
+    if not (config.FUSED_EPILOGUE and w.shape[0] % 4 == 0):
+        y = _TORCH_ACT[act](F.conv2d(x, w, b, stride=st, padding=pd, dilation=dl, groups=groups), slope)
+        if res is not None:
+            y = y + res
+        if post_relu:
+            y = F.relu_(y)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    def own(x):
+        y = F.conv2d(x, w, None, stride=st, padding=pd, dilation=dl, groups=groups)
+        ypm = as_pm(y)
+        o = ops.bias_act(ypm, b, act, slope, res=None if res is None else res.permute(0, 2, 3, 1), post_relu=post_relu,
+                         out=None if out is None else out.permute(0, 2, 3, 1))
+        return as_nchw(o)
+
+    if act == "relu" and res is None and out is None and not post_relu and config.AUTOTUNE:
+        def fused(x):
+            return torch.cudnn_convolution_relu(x, w, b, st, pd, dl, groups).contiguous(memory_format=torch.channels_last)
+        return autotune.pick(("conv_relu", tuple(x.shape), tuple(w.shape), st, pd, dl, groups), (own, fused), x)
+    return own(x)
 
 
 def up2(x):

@@ -215,22 +215,25 @@ def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
     _count(1)
 
 
-def gru_update(q_pm, bias, z, net_view):
+def gru_update(q_pm, bias, z, net_view, net_copy=None):
+    """h = (1-z)*h + z*tanh(q+bias) in place on the state slice; `net_copy` (dense) also receives h."""
     C = z.shape[-1]
     np_, ldn = _pm(net_view)
-    check(_lib.lib().pp_gru_update(_p(_dense(q_pm)), _p(bias), _p(_dense(z)), np_, ldn, z.numel() // C, C, _stream()),
+    check(_lib.lib().pp_gru_update(_p(_dense(q_pm)), _p(bias), _p(_dense(z)), np_, ldn,
+                                   _p(_dense(net_copy)) if net_copy is not None else None, z.numel() // C, C, _stream()),
           "pp_gru_update")
     _count(1)
 
 
-def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view):
-    """mot_pm [..,128] (channels 126,127 ignored), flow_pm [..,2] -> 128-channel slot views of HX and RX."""
+def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view, bias=None):
+    """mot_pm [..,128] (channels 126,127 ignored), flow_pm [..,2] -> 128-channel slot views of HX and RX.
+    With `bias`, mot_pm is the raw conv output and relu(mot + bias) is applied on the way."""
     mp, ldm = _pm(mot_pm)
     p0, ld0 = _pm(d0_view)
     p1, ld1 = _pm(d1_view)
     if ld0 != ld1:
         raise RuntimeError("HX / RX must share the pixel stride")
-    check(_lib.lib().pp_raft_pack_motion(mp, ldm, _p(_dense(flow_pm)), p0, p1, ld0, flow_pm.numel() // 2, _stream()),
+    check(_lib.lib().pp_raft_pack_motion(mp, ldm, _p(bias), _p(_dense(flow_pm)), p0, p1, ld0, flow_pm.numel() // 2, _stream()),
           "pp_raft_pack_motion")
     _count(1)
 
@@ -238,13 +241,39 @@ def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view):
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
 
 
-def bias_act_(x_pm, bias, act="none", slope=0.0):
-    """in-place act(x + bias) on a dense pixel-major tensor [..., C]; returns x_pm."""
+def bias_act(x_pm, bias=None, act="none", slope=0.0, res=None, post_relu=False, out=None):
+    """out = post(act(x + bias) + res) on pixel-major views [..., C] (unit channel stride, dense over pixels; x / res /
+    out may each be a channel slice of a wider buffer).  out=None -> in place on x_pm.  Returns out."""
     C = x_pm.shape[-1]
-    check(_lib.lib().pp_bias_act(_p(_dense(x_pm)), _p(_dense(bias)), x_pm.numel() // C, C, ACT[act], float(slope), _stream()),
-          "pp_bias_act")
+    out = x_pm if out is None else out
+    if out.shape != x_pm.shape or (res is not None and res.shape != x_pm.shape):
+        raise RuntimeError("bias_act: shape mismatch")
+    xp, ldx = _pm(x_pm)
+    op, ldo = _pm(out)
+    rp, ldr = _pm(res) if res is not None else (None, C)
+    check(_lib.lib().pp_bias_act(xp, ldx, _p(bias), rp, ldr, op, ldo, x_pm.numel() // C, C, ACT[act], float(slope),
+                                 int(bool(post_relu)), _stream()), "pp_bias_act")
     _count(1)
-    return x_pm
+    return out
+
+
+def bias_act_(x_pm, bias, act="none", slope=0.0):
+    """in-place act(x + bias); returns x_pm."""
+    return bias_act(x_pm, bias, act, slope)
+
+
+def instance_norm(x_pm, relu=False, res=None, post_relu=False, eps=1e-5, out=None):
+    """InstanceNorm2d(affine=False) on a dense pixel-major map [n,h,w,C] (+ ReLU, + residual add, + final ReLU)."""
+    n, h, w, C = x_pm.shape
+    out = torch.empty_like(x_pm) if out is None else out
+    lib = _lib.lib()
+    nbytes = lib.pp_instance_norm_workspace_bytes(n, h * w, C)
+    ws = torch.empty(max(nbytes // 4, 4), device=x_pm.device, dtype=torch.float32)
+    check(lib.pp_instance_norm(_p(_dense(x_pm)), _p(_dense(res)) if res is not None else None, _p(_dense(out)), n, h * w, C,
+                               float(eps), int(bool(relu)), int(bool(post_relu)), _p(ws), ws.numel() * 4, _stream()),
+          "pp_instance_norm")
+    _count(2)
+    return out
 
 
 def upsample2x(x_pm):

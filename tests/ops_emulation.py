@@ -137,11 +137,33 @@ def install(monkeypatch, hostsim):
         hostsim.hs_composite(_fp(p), _fp(m), ctypes.c_void_p(ori_u8.data_ptr()), ctypes.c_void_p(comp_u8.data_ptr()), n, fr,
                              fs, H, W)
 
+    _act = {"none": lambda t: t, "relu": F.relu, "leaky": None, "sigmoid": torch.sigmoid, "tanh": torch.tanh}
+
+    def bias_act(x_pm, bias=None, act="none", slope=0.0, res=None, post_relu=False, out=None):
+        t = x_pm if bias is None else x_pm + bias
+        t = F.leaky_relu(t, slope) if act == "leaky" else _act[act](t)
+        if res is not None:
+            t = t + res
+        if post_relu:
+            t = F.relu(t)
+        out = x_pm if out is None else out
+        out.copy_(t)
+        return out
+
     def bias_act_(x_pm, bias, act="none", slope=0.0):
-        x_pm.add_(bias)
-        {"none": lambda: None, "relu": lambda: F.relu_(x_pm), "leaky": lambda: F.leaky_relu_(x_pm, slope),
-         "sigmoid": lambda: torch.sigmoid_(x_pm), "tanh": lambda: torch.tanh_(x_pm)}[act]()
-        return x_pm
+        return bias_act(x_pm, bias, act, slope)
+
+    def instance_norm(x_pm, relu=False, res=None, post_relu=False, eps=1e-5, out=None):
+        t = F.instance_norm(x_pm.permute(0, 3, 1, 2), eps=eps).permute(0, 2, 3, 1)
+        if relu:
+            t = F.relu(t)
+        if res is not None:
+            t = t + res
+        if post_relu:
+            t = F.relu(t)
+        out = torch.empty_like(x_pm) if out is None else out
+        out.copy_(t)
+        return out
 
     def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
         C = z_out.shape[-1]
@@ -149,11 +171,14 @@ def install(monkeypatch, hostsim):
         z_out.copy_(g[..., :C])
         rnet_view.copy_(g[..., C:] * net_view)
 
-    def gru_update(q_pm, bias, z, net_view):
+    def gru_update(q_pm, bias, z, net_view, net_copy=None):
         net_view.copy_((1 - z) * net_view + z * torch.tanh(q_pm + bias))
+        if net_copy is not None:
+            net_copy.copy_(net_view)
 
-    def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view):
-        v = torch.cat([mot_pm[..., :126], flow_pm], -1)
+    def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view, bias=None):
+        m = mot_pm if bias is None else F.relu(mot_pm + bias)
+        v = torch.cat([m[..., :126], flow_pm], -1)
         d0_view.copy_(v)
         d1_view.copy_(v)
 

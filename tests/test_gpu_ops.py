@@ -256,6 +256,35 @@ def test_bias_act_and_upsample2x():
         assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
 
 
+def test_bias_act_strided_residual_and_instance_norm():
+    """pp_bias_act with channel-slice views (x / res / out each a slice of a wider pixel-major buffer), residual add and
+    final ReLU vs plain torch; pp_instance_norm vs F.instance_norm (+ReLU, +residual, in place) on the three channel
+    counts of the RAFT feature encoder.  Tolerance 2e-5 abs on O(1) values (fp32 sums, double fold of the partials)."""
+    from propainter_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    X, R, O = (torch.randn(2, 9, 13, 48, generator=g).to(DEV) for _ in range(3))
+    bias = torch.randn(16, generator=g).to(DEV)
+    for act, fn in (("leaky", lambda t: F.leaky_relu(t, 0.1)), ("relu", F.relu), ("none", lambda t: t), ("tanh", torch.tanh)):
+        for post in (False, True):
+            x, r, o = X[..., 16:32], R[..., 32:48], O.clone()
+            want = fn(x + bias) + r
+            want = F.relu(want) if post else want
+            ops.bias_act(x, bias, act, 0.1, res=r, post_relu=post, out=o[..., 0:16])
+            assert torch.allclose(o[..., 0:16], want, atol=1e-6) and torch.equal(o[..., 16:], O[..., 16:])
+    y = X[..., :16].clone()
+    assert torch.allclose(ops.bias_act(y, None, "relu"), F.relu(X[..., :16]), atol=0)          # no bias, in place
+    for n, h, w, C in ((3, 40, 56, 64), (2, 20, 27, 96), (5, 9, 14, 128), (1, 3, 5, 64)):
+        x = (torch.randn(n, h, w, C, generator=g) * 2 + torch.randn(1, 1, 1, C, generator=g) * 3).to(DEV)
+        res = torch.randn(n, h, w, C, generator=g).to(DEV)
+        ref = F.instance_norm(x.permute(0, 3, 1, 2), eps=1e-5).permute(0, 2, 3, 1)
+        assert torch.allclose(ops.instance_norm(x), ref, atol=2e-5)
+        assert torch.allclose(ops.instance_norm(x, relu=True), F.relu(ref), atol=2e-5)
+        want = F.relu(res + F.relu(ref))
+        xin = x.clone()
+        got = ops.instance_norm(xin, relu=True, res=res, post_relu=True, out=xin)
+        assert got.data_ptr() == xin.data_ptr() and torch.allclose(got, want, atol=2e-5)
+
+
 def test_gru_fusion_kernels():
     """SepConvGRU elementwise rules (RAFT/update.py:45-60) on slices of the persistent HX / RX buffers."""
     from propainter_b200 import ops
@@ -271,13 +300,19 @@ def test_gru_fusion_kernels():
     g = torch.sigmoid(zr + bzr)
     assert torch.allclose(z.cpu(), g[..., :C], atol=2e-6) and torch.allclose(rx.cpu()[..., :C], g[..., C:] * HX[..., :C], atol=5e-6)
     assert torch.equal(rx.cpu()[..., C:], RX[..., C:]) and torch.equal(hx.cpu(), HX)
-    ops.gru_update(q.to(DEV), bq.to(DEV), z, hx[..., :C])
+    netc = torch.empty(B, h, w, C, device=DEV)
+    ops.gru_update(q.to(DEV), bq.to(DEV), z, hx[..., :C], net_copy=netc)
     ref = (1 - g[..., :C]) * HX[..., :C] + g[..., :C] * torch.tanh(q + bq)
     assert torch.allclose(hx.cpu()[..., :C], ref, atol=5e-6) and torch.equal(hx.cpu()[..., C:], HX[..., C:])
+    assert torch.equal(netc, hx[..., :C])
     ops.raft_pack_motion(mot.to(DEV), flow.to(DEV), hx[..., 256:], rx[..., 256:])
     want = torch.cat([mot[..., :126], flow], -1)
     assert torch.equal(hx.cpu()[..., 256:], want) and torch.equal(rx.cpu()[..., 256:], want)
     assert torch.equal(hx.cpu()[..., C:256], HX[..., C:256])
+    bm = torch.randn(128, generator=gen)
+    ops.raft_pack_motion(mot.to(DEV), flow.to(DEV), hx[..., 256:], rx[..., 256:], bias=bm.to(DEV))   # raw conv output in
+    want = torch.cat([F.relu(mot + bm)[..., :126], flow], -1)
+    assert torch.allclose(hx.cpu()[..., 256:], want, atol=1e-6) and torch.equal(rx[..., 256:], hx[..., 256:])
 
 
 def test_u8_and_composite():

@@ -33,7 +33,9 @@ def test_param_net_roundtrip_and_half():
     with pytest.raises(RuntimeError):
         b.load_state_dict({k: a.P[k]}, strict=True)                 # strict like the reference loaders
     b.half()
-    assert b.P[k].dtype == torch.float16 and all(not p.requires_grad for p in b.parameters())
+    # .half() halves the storage (state_dict, like the reference's --fp16 nets); the view the kernels read stays fp32
+    assert b.state_dict()[k].dtype == torch.float16 and b.P[k].dtype == torch.float32
+    assert torch.equal(b.P[k], b.state_dict()[k].float()) and all(not p.requires_grad for p in b.parameters())
     raft = ParamNet(schemas.raft_schema(), seed=0)                   # shared norm3 / downsample.1 module
     assert raft.P["cnet.layer2.0.norm3.weight"] is raft.state_dict(keep_vars=True)["cnet.layer2.0.downsample.1.weight"]
 

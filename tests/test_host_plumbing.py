@@ -47,9 +47,12 @@ def test_flow_completion_plumbing(emu):
     assert rel_err(pred[0], ref[0]) < 1e-4 and rel_err(pred[1], ref[1]) < 1e-4, (rel_err(pred[0], ref[0]), rel_err(pred[1], ref[1]))
 
 
-@pytest.mark.parametrize("H,W,t,lt", [(64, 96, 4, 3), (128, 128, 3, 2), (64, 64, 2, 1)])
-def test_generator_plumbing(emu, H, W, t, lt):
+@pytest.mark.parametrize("H,W,t,lt,alt", [(64, 96, 4, 3, False), (128, 128, 3, 2, False), (64, 64, 2, 1, False), (64, 96, 4, 3, True)])
+def test_generator_plumbing(emu, monkeypatch, H, W, t, lt, alt):
+    from propainter_b200 import autotune
     from propainter_b200.model.propainter import InpaintGenerator
+    if alt:      # force the alternative execution plans autotune may pick on the GPU (per-group dense encoder convs)
+        monkeypatch.setattr(autotune, "pick", lambda key, variants, *a, **k: variants[0 if key[0] == "conv_relu" else -1](*a))
     net = InpaintGenerator(seed=3)
     gen = torch.Generator().manual_seed(1)
     frames = torch.rand(1, t, 3, H, W, generator=gen) * 2 - 1
