@@ -100,6 +100,17 @@ size_t pp_ffn_overlap_add_workspace_bytes(int frames, int h, int w, int CH);
 int pp_ffn_overlap_add(const float* Y, int ldy, float* Z, int ldz, int frames, int h, int w, int CH, void* workspace,
                        size_t ws_bytes, cudaStream_t stream);
 
+/* ---- transformer glue ------------------------------------------------------------------------ */
+/* SparseWindowAttention.pool_layer (model/modules/sparse_transformer.py:131-133, used :203-206): depthwise Conv2d with
+ * kernel = stride = (kh,kw), no padding.  x [n][H][W][C] pixel-major (pixel stride ld_x), w_taps [kh*kw][C],
+ * out [n][H/kh][W/kw][C] dense. */
+int pp_pool_depthwise(const float* x, int ld_x, const float* w_taps, const float* bias, float* out, int n, int H, int W, int C,
+                      int kh, int kw, cudaStream_t stream);
+/* TemporalSparseTransformer.forward model/modules/sparse_transformer.py:322-334: x_out = x + delta (residual),
+ * y = LayerNorm(x_out) * gamma + beta, rows of C in {128,256,512,1024} floats.  delta NULL: plain LayerNorm. */
+int pp_add_layernorm(const float* x, const float* delta, const float* gamma, const float* beta, float* x_out, float* y, long rows,
+                     int C, float eps, cudaStream_t stream);
+
 /* ---- RAFT SepConvGRU elementwise fusion (RAFT/update.py:45-60,95-97) ------------------------- */
 /* zr: raw output of the fused z|r gate conv [npix][2C]; net: state slice of HX (ld_net); writes z [npix][C]
  * and r*net into the state slice of RX (ld_r). */

@@ -563,6 +563,101 @@ extern "C" int pp_raft_pack_motion(const float* mot, int ld_mot, const float* bi
   return PP_OK;
 }
 
+// ================================================================ transformer glue
+// pool_layer of SparseWindowAttention (sparse_transformer.py:131-133,203-206): depthwise Conv2d with kernel = stride =
+// pool_size, no padding, on the pixel-major token grid.  x [n][H][W][C] (pixel stride ld_x), w tap-major [kh*kw][C].
+__global__ void __launch_bounds__(256) k_pool_depthwise(const float* __restrict__ x, int ld_x, const float* __restrict__ w,
+    const float* __restrict__ bias, float* __restrict__ out, int n, int H, int W, int C, int kh, int kw, int ph, int pw) {
+  const int c4n = C >> 2;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * ph * pw * c4n) return;
+  const int c = (int)(i % c4n) * 4; long r = i / c4n;
+  const int px = (int)(r % pw); r /= pw; const int py = (int)(r % ph); const int f = (int)(r / ph);
+  float4 acc = *reinterpret_cast<const float4*>(bias + c);
+  for (int a = 0; a < kh; ++a)
+    for (int b = 0; b < kw; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (((long)f * H + (py * kh + a)) * W + (px * kw + b)) * ld_x + c);
+      const float4 k = *reinterpret_cast<const float4*>(w + (long)(a * kw + b) * C + c);
+      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+    }
+  *reinterpret_cast<float4*>(out + i * 4) = acc;
+}
+extern "C" int pp_pool_depthwise(const float* x, int ld_x, const float* w_taps, const float* bias, float* out, int n, int H, int W,
+                                 int C, int kh, int kw, cudaStream_t stream) {
+  if (C % 4 || ld_x % 4 || ((uintptr_t)x & 15) || ((uintptr_t)w_taps & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)out & 15))
+    return PP_ERR_ALIGN;
+  if (kh < 1 || kw < 1 || H < kh || W < kw || n < 1 || ld_x < C) return PP_ERR_SHAPE;
+  const int ph = (H - kh) / kh + 1, pw = (W - kw) / kw + 1;
+  const long total = (long)n * ph * pw * (C / 4);
+  k_pool_depthwise<<<pp_blocks(total, 256), 256, 0, stream>>>(x, ld_x, w_taps, bias, out, n, H, W, C, kh, kw, ph, pw);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// residual add + LayerNorm of TemporalSparseTransformer.forward (sparse_transformer.py:322-334): x_out = x + delta,
+// y = LN(x_out)*gamma + beta in one pass (one warp per token row, statistics two-pass in registers).  delta == NULL:
+// plain LayerNorm (x_out not written).
+template <int NV>
+__global__ void __launch_bounds__(256) k_add_layernorm(const float* __restrict__ x, const float* __restrict__ delta,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x_out, float* __restrict__ y, long rows,
+    float eps) {
+  constexpr int C = NV * 128;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const long off = row * C + (k * 32 + lane) * 4;
+    v[k] = *reinterpret_cast<const float4*>(x + off);
+    if (delta != nullptr) {
+      const float4 d = *reinterpret_cast<const float4*>(delta + off);
+      v[k].x += d.x; v[k].y += d.y; v[k].z += d.z; v[k].w += d.w;
+      *reinterpret_cast<float4*>(x_out + off) = v[k];
+    }
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int ci = (k * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + ci), b = *reinterpret_cast<const float4*>(beta + ci);
+    float4 o;
+    o.x = (v[k].x - mean) * rstd * g.x + b.x; o.y = (v[k].y - mean) * rstd * g.y + b.y;
+    o.z = (v[k].z - mean) * rstd * g.z + b.z; o.w = (v[k].w - mean) * rstd * g.w + b.w;
+    *reinterpret_cast<float4*>(y + row * C + ci) = o;
+  }
+}
+extern "C" int pp_add_layernorm(const float* x, const float* delta, const float* gamma, const float* beta, float* x_out, float* y,
+                                long rows, int C, float eps, cudaStream_t stream) {
+  if (((uintptr_t)x & 15) || ((uintptr_t)delta & 15) || ((uintptr_t)gamma & 15) || ((uintptr_t)beta & 15) ||
+      ((uintptr_t)x_out & 15) || ((uintptr_t)y & 15)) return PP_ERR_ALIGN;
+  if (rows < 0 || (delta != nullptr && x_out == nullptr)) return PP_ERR_SHAPE;
+  if (rows == 0) return PP_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  switch (C) {
+    case 128: k_add_layernorm<1><<<grid, 256, 0, stream>>>(x, delta, gamma, beta, x_out, y, rows, eps); break;
+    case 256: k_add_layernorm<2><<<grid, 256, 0, stream>>>(x, delta, gamma, beta, x_out, y, rows, eps); break;
+    case 512: k_add_layernorm<4><<<grid, 256, 0, stream>>>(x, delta, gamma, beta, x_out, y, rows, eps); break;
+    case 1024: k_add_layernorm<8><<<grid, 256, 0, stream>>>(x, delta, gamma, beta, x_out, y, rows, eps); break;
+    default: return PP_ERR_SHAPE;
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 // ================================================================ mask preparation
 __global__ void __launch_bounds__(256) k_mask_dilate(const uint8_t* __restrict__ src, float* __restrict__ dst, int T, int H,
                                                      int W, int iterations) {

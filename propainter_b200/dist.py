@@ -142,12 +142,12 @@ class ShardedProPainter:
         if mine:
             enc_ids = sorted({f for wi in mine for f in plan[wi][0] + plan[wi][1]})
             pos = {f: i for i, f in enumerate(enc_ids)}
-            enc = pipe.model.encode(upd_f[0, enc_ids], md[enc_ids], upd_m[0, enc_ids])
+            enc = pipe.model.encode(upd_f[0, enc_ids], md[enc_ids], upd_m[0, enc_ids]).permute(0, 2, 3, 1)   # pixel-major
             for wi in mine:
                 nb, refs = plan[wi]
                 ids = nb + refs
                 sel = [pos[f] for f in ids]
-                preds[wi] = pipe.model.forward_features(enc[sel], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                preds[wi] = pipe.model.forward_features(enc[sel].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
                                                         md[ids], upd_m[0, ids], len(nb))
         # seam state from the previous non-empty rank: every frame visited by an earlier window
         earlier = sorted({f for wi in range(len(plan)) if owner[wi] < self.rank for f in plan[wi][0]})

@@ -164,13 +164,13 @@ class ProPainterPipeline:
         visited = [False] * T if visited is None else visited
         md = masks_dilated[0].contiguous()
         # encoder features depend only on (frame, mask, updated mask): computed once per clip, not once per window
-        enc_all = self.model.encode(upd_frames[0], md, upd_masks[0])
+        enc_all = self.model.encode(upd_frames[0], md, upd_masks[0]).permute(0, 2, 3, 1)     # pixel-major rows: cheap frame gather
         todo = [(wi, nb, refs) for wi, (nb, refs) in enumerate(plan) if windows is None or wi in windows]
         nfl = max(1, int(cfg.windows_in_flight)) if upd_frames.is_cuda else 1
         if nfl == 1:
             for wi, nb, refs in todo:
                 ids = nb + refs
-                pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                pred = self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
                                                    md[ids], upd_masks[0, ids], len(nb))
                 ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
                 for i in nb:
@@ -199,7 +199,7 @@ class ProPainterPipeline:
             st = self._side_streams[slot]
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                pred = self.model.forward_features(enc_all[ids], (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                pred = self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
                                                    md[ids], upd_masks[0, ids], len(nb), slot=slot)
             pending.append((slot, nb, pred))
         drain(0)

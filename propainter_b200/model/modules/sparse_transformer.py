@@ -57,7 +57,8 @@ class TransformerExec:
             b = torch.cat([P[p + "query.bias"], P[p + "key.bias"], P[p + "value.bias"]], 0).contiguous()
             wkv = torch.cat([P[p + "key.weight"], P[p + "value.weight"]], 0).contiguous()
             bkv = torch.cat([P[p + "key.bias"], P[p + "value.bias"]], 0).contiguous()
-            return w, b, wkv, bkv, cl(P[p + "pool_layer.weight"]), P[p + "pool_layer.bias"].contiguous()
+            wpool = P[p + "pool_layer.weight"]                                     # [C,1,kh,kw] -> tap-major [kh*kw, C]
+            return w, b, wkv, bkv, wpool.reshape(wpool.shape[0], -1).t().contiguous(), P[p + "pool_layer.bias"].contiguous()
         return self.net.packed(f"qkv{i}", build)
 
     def _ffn(self, i):
@@ -96,25 +97,30 @@ class TransformerExec:
         NT = H2 * W2
         key_tok = self.net.packed(f"ktab:{H2}x{W2}", lambda: torch.from_numpy(window_key_table(H2, W2, WIN)).to(tokens.device))
         P = self.net.P
-        x = tokens
+        x = tokens.contiguous()
         pad = (H2 != fh) or (W2 != fw)
+        norm = lambda i, k: (P[f"transformers.transformer.{i}.norm{k}.weight"], P[f"transformers.transformer.{i}.norm{k}.bias"])
+        _, y = ops.add_layernorm(x, None, *norm(0, 1))
         for i in range(self.depths):
             p = f"transformers.transformer.{i}."
             wqkv, bqkv, wkv, bkv, wpool, bpool = self._qkv(i)
-            y = F.layer_norm(x, (C,), P[p + "norm1.weight"], P[p + "norm1.bias"])
             if pad:                                                    # zeros are padded *before* q/k/v (:168-176)
                 y = F.pad(y, (0, 0, 0, W2 - fw, 0, H2 - fh))
             qkv = F.linear(y, wqkv, bqkv).view(t, NT, 3 * C)
-            pooled = as_pm(F.conv2d(as_nchw(y), wpool, bpool, stride=POOL, groups=C))           # [t,ph,pw,C]
+            pooled = ops.pool_depthwise(y, wpool, bpool, POOL[0], POOL[1])                      # [t,ph,pw,C]
             pool_kv = F.linear(pooled.reshape(t, -1, C), wkv, bkv)                              # [t,NP,2C]
             att = ops.sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, i % t_dilation, t_dilation,
                                          WN=WIN[0] * WIN[1], C=C).view(t, H2, W2, C)
             if pad:
                 att = att[:, :fh, :fw]
-            x = x + F.linear(att, P[p + "attention.proj.weight"], P[p + "attention.proj.bias"])
+            # x = x + proj(att); y = norm2(x)   (residual add fused into the LayerNorm pass)
+            x, y = ops.add_layernorm(x, F.linear(att, P[p + "attention.proj.weight"], P[p + "attention.proj.bias"]), *norm(i, 2))
             w1, b1, w2, b2 = self._ffn(i)
-            y = F.layer_norm(x, (C,), P[p + "norm2.weight"], P[p + "norm2.bias"])
             hdn = F.linear(y.reshape(t * fh * fw, C), w1, b1)
             hdn = ops.ffn_overlap_add(hdn, t, hw[0], hw[1], self.ffn_ch)
-            x = x + F.linear(hdn, w2, b2).view(t, fh, fw, C)
+            d = F.linear(hdn, w2, b2).view(t, fh, fw, C)
+            if i + 1 < self.depths:                                    # x = x + mlp(y); y = norm1 of the next block
+                x, y = ops.add_layernorm(x, d, *norm(i + 1, 1))
+            else:
+                x = x + d
         return x

@@ -262,6 +262,28 @@ def bias_act_(x_pm, bias, act="none", slope=0.0):
     return bias_act(x_pm, bias, act, slope)
 
 
+def pool_depthwise(x_pm, w_taps, bias, kh, kw):
+    """depthwise conv, kernel = stride = (kh,kw): x_pm [n,H,W,C] -> [n,H//kh,W//kw,C]; w_taps [kh*kw, C]."""
+    n, H, W, C = x_pm.shape
+    xp, ld = _pm(x_pm)
+    out = torch.empty(n, (H - kh) // kh + 1, (W - kw) // kw + 1, C, device=x_pm.device, dtype=torch.float32)
+    check(_lib.lib().pp_pool_depthwise(xp, ld, _p(_dense(w_taps)), _p(bias), _p(out), n, H, W, C, kh, kw, _stream()),
+          "pp_pool_depthwise")
+    _count(1)
+    return out
+
+
+def add_layernorm(x, delta, gamma, beta, eps=1e-5):
+    """(x + delta, LayerNorm(x + delta)) over the last dim; delta=None -> (x, LayerNorm(x)).  Dense tensors."""
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    xo = torch.empty_like(x) if delta is not None else None
+    check(_lib.lib().pp_add_layernorm(_p(_dense(x)), _p(_dense(delta)) if delta is not None else None, _p(gamma), _p(beta),
+                                      _p(xo), _p(y), x.numel() // C, C, float(eps), _stream()), "pp_add_layernorm")
+    _count(1)
+    return (xo if delta is not None else x), y
+
+
 def instance_norm(x_pm, relu=False, res=None, post_relu=False, eps=1e-5, out=None):
     """InstanceNorm2d(affine=False) on a dense pixel-major map [n,h,w,C] (+ ReLU, + residual add, + final ReLU)."""
     n, h, w, C = x_pm.shape

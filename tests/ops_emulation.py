@@ -153,6 +153,15 @@ def install(monkeypatch, hostsim):
     def bias_act_(x_pm, bias, act="none", slope=0.0):
         return bias_act(x_pm, bias, act, slope)
 
+    def pool_depthwise(x_pm, w_taps, bias, kh, kw):
+        C = x_pm.shape[-1]
+        w = w_taps.t().reshape(C, 1, kh, kw)
+        return F.conv2d(x_pm.permute(0, 3, 1, 2), w, bias, stride=(kh, kw), groups=C).permute(0, 2, 3, 1).contiguous()
+
+    def add_layernorm(x, delta, gamma, beta, eps=1e-5):
+        xo = x if delta is None else x + delta
+        return xo, F.layer_norm(xo, (x.shape[-1],), gamma, beta, eps)
+
     def instance_norm(x_pm, relu=False, res=None, post_relu=False, eps=1e-5, out=None):
         t = F.instance_norm(x_pm.permute(0, 3, 1, 2), eps=eps).permute(0, 2, 3, 1)
         if relu:

@@ -285,6 +285,26 @@ def test_bias_act_strided_residual_and_instance_norm():
         assert got.data_ptr() == xin.data_ptr() and torch.allclose(got, want, atol=2e-5)
 
 
+def test_transformer_glue_kernels():
+    """pp_pool_depthwise vs F.conv2d(groups=C, kernel=stride) (sparse_transformer.py:131-133) and pp_add_layernorm vs
+    x + d followed by F.layer_norm (:322-334); fp32, 1e-5."""
+    from propainter_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for (n, H, W, C, kh, kw) in ((3, 20, 36, 512, 4, 4), (2, 15, 18, 128, 4, 4), (1, 10, 9, 64, 2, 3)):
+        x = torch.randn(n, H, W, C, generator=g)
+        w, b = torch.randn(C, 1, kh, kw, generator=g) * 0.3, torch.randn(C, generator=g)
+        ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=(kh, kw), groups=C).permute(0, 2, 3, 1)
+        got = ops.pool_depthwise(x.to(DEV), w.reshape(C, -1).t().contiguous().to(DEV), b.to(DEV), kh, kw).cpu()
+        assert got.shape == ref.shape and torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+    for (rows, C) in (((3, 20, 36), 512), ((7, 5), 128), ((1, 1), 1024)):
+        x, d = torch.randn(*rows, C, generator=g) * 2 + 0.5, torch.randn(*rows, C, generator=g)
+        ga, be = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        xo, y = ops.add_layernorm(x.to(DEV), d.to(DEV), ga.to(DEV), be.to(DEV))
+        assert torch.equal(xo.cpu(), x + d) and torch.allclose(y.cpu(), F.layer_norm(x + d, (C,), ga, be), atol=1e-5, rtol=1e-5)
+        x2, y2 = ops.add_layernorm(x.to(DEV), None, ga.to(DEV), be.to(DEV))
+        assert torch.equal(x2.cpu(), x) and torch.allclose(y2.cpu(), F.layer_norm(x, (C,), ga, be), atol=1e-5, rtol=1e-5)
+
+
 def test_gru_fusion_kernels():
     """SepConvGRU elementwise rules (RAFT/update.py:45-60) on slices of the persistent HX / RX buffers."""
     from propainter_b200 import ops
