@@ -113,13 +113,15 @@ int pp_add_layernorm(const float* x, const float* delta, const float* gamma, con
 
 /* ---- RAFT SepConvGRU elementwise fusion (RAFT/update.py:45-60,95-97) ------------------------- */
 /* zr: raw output of the fused z|r gate conv [npix][2C]; net: state slice of HX (ld_net); writes z [npix][C]
- * and r*net into the state slice of RX (ld_r). */
-int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet, int ld_r,
-                long npix, int C, cudaStream_t stream);
-/* net = (1-z)*net + z*tanh(q + bias), in place on the state slice of HX; net_copy (nullable, dense [npix][C]) also
+ * and r*net into the state slice of RX (ld_r).  bias [2C] and pre [npix][2C] are nullable addends: `pre` carries the
+ * part of the gate convs that does not change over the refinement iterations (the context-feature input channels,
+ * RAFT/update.py:129), convolved once per clip. */
+int pp_gru_gate(const float* zr, const float* bias, const float* pre, const float* net, int ld_net, float* z, float* rnet,
+                int ld_r, long npix, int C, cudaStream_t stream);
+/* net = (1-z)*net + z*tanh(q + bias + pre), in place on the state slice of HX; net_copy (nullable, dense [npix][C]) also
  * receives the new state (input of the flow / mask heads, RAFT/update.py:133-136). */
-int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, float* net_copy, long npix, int C,
-                  cudaStream_t stream);
+int pp_gru_update(const float* q, const float* bias, const float* pre, const float* z, float* net, int ld_net, float* net_copy,
+                  long npix, int C, cudaStream_t stream);
 /* motion features: channels [0,126) of `mot` + the 2 flow channels -> the same 128-channel slot of d0 and d1.
  * bias != NULL: `mot` is the raw conv output and relu(mot + bias) (RAFT/update.py:96) is applied on the way. */
 int pp_raft_pack_motion(const float* mot, int ld_mot, const float* bias, const float* flow, float* d0, float* d1, int ld,

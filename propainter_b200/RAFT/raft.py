@@ -53,13 +53,20 @@ class RAFT(ParamNet):
             return cl(w), torch.cat([b, b.new_zeros(2)]).contiguous()
         return self.packed("motion_out", build)
 
-    def _gates(self, tag):
+    def _gru(self, tag):
+        """SepConvGRU weights of one pass (update.py:45-60), input channels [h(128) | inp(128) | motion(128)] (:129-130).
+        z and r share one conv.  The `inp` (context) channels do not change over the refinement iterations, so their
+        share of every gate conv is split off: (w_zr, w_q) act on the per-iteration [h | motion] buffers, (w_zr_inp,
+        b_zr) / (w_q_inp, b_q) are convolved with `inp` once per clip and enter through the gate kernels' `pre` term."""
         def build():
             u = "update_block.gru."
-            w = torch.cat([self.P[u + f"convz{tag}.weight"], self.P[u + f"convr{tag}.weight"]], 0)
-            b = torch.cat([self.P[u + f"convz{tag}.bias"], self.P[u + f"convr{tag}.bias"]], 0)
-            return cl(w), b.contiguous()
-        return self.packed("zr" + tag, build)
+            wzr = torch.cat([self.P[u + f"convz{tag}.weight"], self.P[u + f"convr{tag}.weight"]], 0)
+            bzr = torch.cat([self.P[u + f"convz{tag}.bias"], self.P[u + f"convr{tag}.bias"]], 0)
+            wq, bq = self.P[u + f"convq{tag}.weight"], self.P[u + f"convq{tag}.bias"]
+            dyn = lambda w: cl(torch.cat([w[:, :128], w[:, 256:]], 1))
+            ctx = lambda w: cl(w[:, 128:256])
+            return dyn(wzr), dyn(wq), (ctx(wzr), bzr.contiguous()), (ctx(wq), bq.contiguous())
+        return self.packed("gru" + tag, build)
 
     # ------------------------------------------------------------------ encoders (extractor.py:168-192)
     def _encode(self, p, x):
@@ -112,12 +119,15 @@ class RAFT(ParamNet):
         u = "update_block."
         corr = torch.empty(B, h, w, 324, device=dev)
         # persistent GRU buffers (no torch.cat inside the loop):
-        #   HX = [net | inp | motion(126) flow(2)]  -> z/r gate convs;   RX = [r*net | inp | motion flow] -> candidate conv
-        HX = torch.empty(B, h, w, 384, device=dev)
-        RX = torch.empty(B, h, w, 384, device=dev)
+        #   HX = [net | motion(126) flow(2)]  -> z/r gate convs;   RX = [r*net | motion flow] -> candidate conv
+        # the context channels `inp` are iteration-invariant: their conv contributions (+ biases) are computed here, once
+        HX = torch.empty(B, h, w, 256, device=dev)
+        RX = torch.empty(B, h, w, 256, device=dev)
         HX[..., :128] = as_pm(net)
-        HX[..., 128:256] = as_pm(inp)
-        RX[..., 128:256] = HX[..., 128:256]
+        pre = {}
+        for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
+            _, _, zr_ctx, q_ctx = self._gru(tag)
+            pre[tag] = (as_pm(conv(inp, zr_ctx, 1, pad)), as_pm(conv(inp, q_ctx, 1, pad)))
         netv, z = HX[..., :128], torch.empty(B, h, w, 128, device=dev)
         netc = torch.empty(B, h, w, 128, device=dev)            # dense copy of the state for the flow / mask heads
         mot_in = torch.empty(B, h, w, 256, device=dev)          # [cor(192) | flo(64)] without a torch.cat (update.py:95)
@@ -131,13 +141,12 @@ class RAFT(ParamNet):
             flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
             conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu", out=as_nchw(mot_in[..., 192:]))
             mot = F.conv2d(as_nchw(mot_in), mw, None, padding=1)                   # 126 real + 2 pad channels, raw
-            ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 256:], RX[..., 256:], bias=mb)   # + bias + ReLU (update.py:96)
+            ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 128:], RX[..., 128:], bias=mb)   # + bias + ReLU (update.py:96)
             for tag, pad in (("1", (0, 2)), ("2", (2, 0))):
-                gw, gb = self._gates(tag)
-                qw, qb = self._wb(u + f"gru.convq{tag}")
-                ops.gru_gate(as_pm(F.conv2d(as_nchw(HX), gw, None, padding=pad)), gb, netv, z, RX[..., :128])
-                ops.gru_update(as_pm(F.conv2d(as_nchw(RX), qw, None, padding=pad)), qb, z, netv,
-                               net_copy=netc if tag == "2" else None)
+                gw, qw, _, _ = self._gru(tag)
+                ops.gru_gate(as_pm(F.conv2d(as_nchw(HX), gw, None, padding=pad)), None, netv, z, RX[..., :128], pre=pre[tag][0])
+                ops.gru_update(as_pm(F.conv2d(as_nchw(RX), qw, None, padding=pad)), None, z, netv,
+                               net_copy=netc if tag == "2" else None, pre=pre[tag][1])
             net = as_nchw(netc)
             d = conv(conv(net, self._wb(u + "flow_head.conv1"), 1, 1, act="relu"), self._wb(u + "flow_head.conv2"), 1, 1)
             c1 = c1 + as_pm(d)

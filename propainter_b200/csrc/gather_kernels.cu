@@ -494,13 +494,19 @@ extern "C" int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h
 //   RX = [r*net | inp | motion | flow] (input of the candidate conv)
 // so no torch.cat is needed inside the 20-iteration loop.
 __global__ void __launch_bounds__(256) k_gru_gate(const float* __restrict__ zr, const float* __restrict__ bias,
-    const float* __restrict__ net, int ld_net, float* __restrict__ z, float* __restrict__ rnet, int ld_r, long npix, int C) {
+    const float* __restrict__ pre, const float* __restrict__ net, int ld_net, float* __restrict__ z, float* __restrict__ rnet,
+    int ld_r, long npix, int C) {
   const int c4n = C >> 2;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * c4n) return;
   const long pix = i / c4n; const int c = (int)(i - pix * c4n) * 4;
-  const float4 zv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + c), rv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + C + c);
-  const float4 bz = *reinterpret_cast<const float4*>(bias + c), br = *reinterpret_cast<const float4*>(bias + C + c);
+  float4 zv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + c), rv = *reinterpret_cast<const float4*>(zr + pix * 2 * C + C + c);
+  float4 bz = make_float4(0.f, 0.f, 0.f, 0.f), br = bz;
+  if (bias != nullptr) { bz = *reinterpret_cast<const float4*>(bias + c); br = *reinterpret_cast<const float4*>(bias + C + c); }
+  if (pre != nullptr) {           // iteration-invariant part of the gate convs (context features), precomputed per pixel
+    const float4 pz = *reinterpret_cast<const float4*>(pre + pix * 2 * C + c), pr = *reinterpret_cast<const float4*>(pre + pix * 2 * C + C + c);
+    zv.x += pz.x; zv.y += pz.y; zv.z += pz.z; zv.w += pz.w; rv.x += pr.x; rv.y += pr.y; rv.z += pr.z; rv.w += pr.w;
+  }
   const float4 h = *reinterpret_cast<const float4*>(net + pix * ld_net + c);
   float4 zo, ro;
   zo.x = 1.0f / (1.0f + expf(-(zv.x + bz.x))); zo.y = 1.0f / (1.0f + expf(-(zv.y + bz.y)));
@@ -511,12 +517,18 @@ __global__ void __launch_bounds__(256) k_gru_gate(const float* __restrict__ zr, 
   *reinterpret_cast<float4*>(rnet + pix * ld_r + c) = ro;
 }
 __global__ void __launch_bounds__(256) k_gru_update(const float* __restrict__ q, const float* __restrict__ bias,
-    const float* __restrict__ z, float* __restrict__ net, int ld_net, float* __restrict__ net_copy, long npix, int C) {
+    const float* __restrict__ pre, const float* __restrict__ z, float* __restrict__ net, int ld_net, float* __restrict__ net_copy,
+    long npix, int C) {
   const int c4n = C >> 2;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * c4n) return;
   const long pix = i / c4n; const int c = (int)(i - pix * c4n) * 4;
-  const float4 qv = *reinterpret_cast<const float4*>(q + pix * C + c), b = *reinterpret_cast<const float4*>(bias + c);
+  float4 qv = *reinterpret_cast<const float4*>(q + pix * C + c), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias != nullptr) b = *reinterpret_cast<const float4*>(bias + c);
+  if (pre != nullptr) {
+    const float4 pq = *reinterpret_cast<const float4*>(pre + pix * C + c);
+    qv.x += pq.x; qv.y += pq.y; qv.z += pq.z; qv.w += pq.w;
+  }
   const float4 zv = *reinterpret_cast<const float4*>(z + pix * C + c);
   float4 h = *reinterpret_cast<float4*>(net + pix * ld_net + c);
   h.x = (1.0f - zv.x) * h.x + zv.x * tanhf(qv.x + b.x); h.y = (1.0f - zv.y) * h.y + zv.y * tanhf(qv.y + b.y);
@@ -525,18 +537,18 @@ __global__ void __launch_bounds__(256) k_gru_update(const float* __restrict__ q,
   if (net_copy != nullptr) *reinterpret_cast<float4*>(net_copy + pix * C + c) = h;   // dense copy for the flow / mask heads
 }
 // z = sigmoid(conv_z), r*h (update.py:47-49 / :54-56): zr = raw output of the fused z|r conv [npix][2C]
-extern "C" int pp_gru_gate(const float* zr, const float* bias, const float* net, int ld_net, float* z, float* rnet,
-                           int ld_r, long npix, int C, cudaStream_t stream) {
-  if (C % 4 || ld_net % 4 || ld_r % 4) return PP_ERR_ALIGN;
-  k_gru_gate<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(zr, bias, net, ld_net, z, rnet, ld_r, npix, C);
+extern "C" int pp_gru_gate(const float* zr, const float* bias, const float* pre, const float* net, int ld_net, float* z,
+                           float* rnet, int ld_r, long npix, int C, cudaStream_t stream) {
+  if (C % 4 || ld_net % 4 || ld_r % 4 || ((uintptr_t)pre & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
+  k_gru_gate<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(zr, bias, pre, net, ld_net, z, rnet, ld_r, npix, C);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 // h = (1-z)*h + z*tanh(conv_q) in place (update.py:50-51 / :57-58); net_copy (nullable) also receives h densely
-extern "C" int pp_gru_update(const float* q, const float* bias, const float* z, float* net, int ld_net, float* net_copy,
-                             long npix, int C, cudaStream_t stream) {
-  if (C % 4 || ld_net % 4 || ((uintptr_t)net_copy & 15)) return PP_ERR_ALIGN;
-  k_gru_update<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(q, bias, z, net, ld_net, net_copy, npix, C);
+extern "C" int pp_gru_update(const float* q, const float* bias, const float* pre, const float* z, float* net, int ld_net,
+                             float* net_copy, long npix, int C, cudaStream_t stream) {
+  if (C % 4 || ld_net % 4 || ((uintptr_t)net_copy & 15) || ((uintptr_t)pre & 15) || ((uintptr_t)bias & 15)) return PP_ERR_ALIGN;
+  k_gru_update<<<pp_blocks(npix * (C / 4), 256), 256, 0, stream>>>(q, bias, pre, z, net, ld_net, net_copy, npix, C);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

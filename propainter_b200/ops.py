@@ -205,21 +205,22 @@ def ffn_overlap_add(Y, frames, h, w, CH=40):
     return Z
 
 
-def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
-    """zr_pm [..,2C] raw gate conv output; net_view / rnet_view: C-channel slices of HX / RX; z_out dense [..,C]."""
+def gru_gate(zr_pm, bias, net_view, z_out, rnet_view, pre=None):
+    """zr_pm [..,2C] raw gate conv output; net_view / rnet_view: C-channel slices of HX / RX; z_out dense [..,C];
+    bias [2C] / pre [..,2C] optional addends."""
     C = z_out.shape[-1]
     np_, ldn = _pm(net_view)
     rp, ldr = _pm(rnet_view)
-    check(_lib.lib().pp_gru_gate(_p(_dense(zr_pm)), _p(bias), np_, ldn, _p(_dense(z_out)), rp, ldr, z_out.numel() // C, C,
-                                 _stream()), "pp_gru_gate")
+    check(_lib.lib().pp_gru_gate(_p(_dense(zr_pm)), _p(bias), _p(_dense(pre)) if pre is not None else None, np_, ldn,
+                                 _p(_dense(z_out)), rp, ldr, z_out.numel() // C, C, _stream()), "pp_gru_gate")
     _count(1)
 
 
-def gru_update(q_pm, bias, z, net_view, net_copy=None):
-    """h = (1-z)*h + z*tanh(q+bias) in place on the state slice; `net_copy` (dense) also receives h."""
+def gru_update(q_pm, bias, z, net_view, net_copy=None, pre=None):
+    """h = (1-z)*h + z*tanh(q+bias+pre) in place on the state slice; `net_copy` (dense) also receives h."""
     C = z.shape[-1]
     np_, ldn = _pm(net_view)
-    check(_lib.lib().pp_gru_update(_p(_dense(q_pm)), _p(bias), _p(_dense(z)), np_, ldn,
+    check(_lib.lib().pp_gru_update(_p(_dense(q_pm)), _p(bias), _p(_dense(pre)) if pre is not None else None, _p(_dense(z)), np_, ldn,
                                    _p(_dense(net_copy)) if net_copy is not None else None, z.numel() // C, C, _stream()),
           "pp_gru_update")
     _count(1)

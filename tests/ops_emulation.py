@@ -174,14 +174,14 @@ def install(monkeypatch, hostsim):
         out.copy_(t)
         return out
 
-    def gru_gate(zr_pm, bias, net_view, z_out, rnet_view):
+    def gru_gate(zr_pm, bias, net_view, z_out, rnet_view, pre=None):
         C = z_out.shape[-1]
-        g = torch.sigmoid(zr_pm + bias)
+        g = torch.sigmoid(zr_pm + (0 if bias is None else bias) + (0 if pre is None else pre))
         z_out.copy_(g[..., :C])
         rnet_view.copy_(g[..., C:] * net_view)
 
-    def gru_update(q_pm, bias, z, net_view, net_copy=None):
-        net_view.copy_((1 - z) * net_view + z * torch.tanh(q_pm + bias))
+    def gru_update(q_pm, bias, z, net_view, net_copy=None, pre=None):
+        net_view.copy_((1 - z) * net_view + z * torch.tanh(q_pm + (0 if bias is None else bias) + (0 if pre is None else pre)))
         if net_copy is not None:
             net_copy.copy_(net_view)
 

@@ -329,6 +329,14 @@ def test_gru_fusion_kernels():
     want = torch.cat([mot[..., :126], flow], -1)
     assert torch.equal(hx.cpu()[..., 256:], want) and torch.equal(rx.cpu()[..., 256:], want)
     assert torch.equal(hx.cpu()[..., C:256], HX[..., C:256])
+    # iteration-invariant addend `pre` instead of the per-channel bias (context-channel share of the gate convs)
+    pz, pq = torch.randn(B, h, w, 2 * C, generator=gen), torch.randn(B, h, w, C, generator=gen)
+    hx2, rx2, z2 = HX.to(DEV), RX.to(DEV), torch.empty(B, h, w, C, device=DEV)
+    ops.gru_gate(zr.to(DEV), None, hx2[..., :C], z2, rx2[..., :C], pre=pz.to(DEV))
+    g2 = torch.sigmoid(zr + pz)
+    assert torch.allclose(z2.cpu(), g2[..., :C], atol=2e-6) and torch.allclose(rx2.cpu()[..., :C], g2[..., C:] * HX[..., :C], atol=5e-6)
+    ops.gru_update(q.to(DEV), None, z2, hx2[..., :C], pre=pq.to(DEV))
+    assert torch.allclose(hx2.cpu()[..., :C], (1 - g2[..., :C]) * HX[..., :C] + g2[..., :C] * torch.tanh(q + pq), atol=5e-6)
     bm = torch.randn(128, generator=gen)
     ops.raft_pack_motion(mot.to(DEV), flow.to(DEV), hx[..., 256:], rx[..., 256:], bias=bm.to(DEV))   # raw conv output in
     want = torch.cat([F.relu(mot + bm)[..., :126], flow], -1)
