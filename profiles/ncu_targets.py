@@ -1,7 +1,8 @@
 """Launches the hot kernels once each at BASELINE configs[1] (C2, 432x240) shapes for ncu:
 
-  ncu --set full --clock-control none --import-source on -k regex:'k_deform_align|k_sparse_attn|k_corr_lookup' \
-      -o gpurun_out/prof python profiles/ncu_targets.py
+  ncu --set full --clock-control none --import-source on \
+      -k regex:'k_deform|k_sparse_attn|k_corr_lookup|k_inorm|k_add_layernorm|k_pool_depthwise|k_bias_act|k_gru' \
+      -o gpurun_out/prof python profiles/ncu_targets.py          (then profiles/ncu_summarize.py on the report)
 
 and, with --time, prints CUDA-event timings of the same launches (never report numbers taken under ncu)."""
 import os
@@ -82,6 +83,25 @@ fr = torch.randn(80, 3, 240, 432, device=dev)
 ff, fb, mk = torch.randn(79, 2, 240, 432, device=dev), torch.randn(79, 2, 240, 432, device=dev), torch.zeros(80, 1, 240, 432, device=dev)
 mk[:, :, 80:160, 150:280] = 1
 run("img_prop_scan_80f", lambda: ops.img_prop_scan(fr, ff, fb, mk, True), reps=5)
+
+# ---- epilogue / glue kernels at their largest call sites
+B2 = 158
+zr, pz = torch.randn(B2, 30, 54, 256, device=dev), torch.randn(B2, 30, 54, 256, device=dev)
+HX, RX = torch.randn(B2, 30, 54, 256, device=dev), torch.randn(B2, 30, 54, 256, device=dev)
+zb, qv, pq = torch.empty(B2, 30, 54, 128, device=dev), torch.randn(B2, 30, 54, 128, device=dev), torch.randn(B2, 30, 54, 128, device=dev)
+run("gru_gate_158pairs", lambda: ops.gru_gate(zr, None, HX[..., :128], zb, RX[..., :128], pre=pz))
+run("gru_update_158pairs", lambda: ops.gru_update(qv, None, zb, HX[..., :128], pre=pq))
+xin = torch.randn(80, 120, 216, 64, device=dev)
+res = torch.randn(80, 120, 216, 64, device=dev)
+run("instance_norm_80x120x216x64", lambda: ops.instance_norm(xin, relu=True, res=res, post_relu=True, out=xin), reps=5)
+cb = torch.randn(B2, 30, 54, 256, device=dev)
+bias256 = torch.randn(256, device=dev)
+run("bias_act_158x30x54x256", lambda: ops.bias_act(cb, bias256, "relu"))
+tok, dl = torch.randn(18, 20, 36, 512, device=dev), torch.randn(18, 20, 36, 512, device=dev)
+gam, bet = torch.randn(512, device=dev), torch.randn(512, device=dev)
+run("add_layernorm_18x720x512", lambda: ops.add_layernorm(tok, dl, gam, bet))
+wt, bp = torch.randn(16, 512, device=dev), torch.randn(512, device=dev)
+run("pool_depthwise_18x20x36x512", lambda: ops.pool_depthwise(tok, wt, bp, 4, 4))
 
 if TIME:
     for k, (med, mn) in results.items():
