@@ -181,7 +181,8 @@ def roofline_probe(torch, pipe, wl):
 
     Primary entry = the tensor-core kernel the north star names (sparse window attention, tcgen05/TMEM); the
     `others` list carries the HBM-bound RAFT lookup and the deformable alignment.  ncu DRAM traffic figures
-    (`traffic`) come from the committed captures under profiles/ (they cannot be measured outside a profiler)."""
+    (`traffic`) come from the committed capture profiles/r1_ncu_final_kernels.csv (dram read + write per launch; the
+    lookup figure is the 22-pair capture scaled to the batch; they cannot be measured outside a profiler)."""
     from propainter_b200 import ops
     from propainter_b200.window_index import padded_grid, token_grid, window_key_table
     hbm, bf16, src = peaks()
@@ -204,7 +205,7 @@ def roofline_probe(torch, pipe, wl):
     ms = _time_kernel(torch, lambda: ops.sparse_window_attn(qkv, pool, ktab, flags, t, H2 * W2, 0, 2))
     ach = flops / (ms * 1e-3) / 1e12
     primary = {"kernel": "k_sparse_attn_umma (+ unmasked-window kernel)", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": 29.6e6, "peak_source": src + " bf16_tflops / 2 (TF32)",
+               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": 29.65e6, "peak_source": src + " bf16_tflops / 2 (TF32)",
                "launch_ms": ms, "algorithmic_flops": flops, "masked_windows": f"{nmask} of {nwin}"}
     # ---- RAFT correlation lookup, one refinement step of the whole clip
     h, w = wl["H"] // 8, wl["W"] // 8
@@ -229,9 +230,9 @@ def roofline_probe(torch, pipe, wl):
     fl_d = Hh * Ww * 9 * 128 * 128 * 2
     primary["others"] = [
         {"kernel": "k_corr_lookup_tma", "bound": "hbm", "achieved": ach_l, "peak": hbm, "unit": "GB/s", "frac": ach_l / hbm,
-         "traffic": 142.3e6 * B / 22, "launch_ms": ms_l, "algorithmic_bytes": alg},
+         "traffic": 124.8e6 * B / 22, "launch_ms": ms_l, "algorithmic_bytes": alg},
         {"kernel": "k_deform_align (+ split-K reduce)", "bound": "tensor", "achieved": fl_d / (ms_d * 1e-3) / 1e12, "peak": tf32_peak,
-         "unit": "TFLOP/s", "frac": fl_d / (ms_d * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_d,
+         "unit": "TFLOP/s", "frac": fl_d / (ms_d * 1e-3) / 1e12 / tf32_peak, "traffic": 36.7e6, "launch_ms": ms_d,
          "algorithmic_flops": fl_d, "note": "warp-level mma.sync TF32 (legacy tensor path), latency-bound gather"}]
     return primary
 
