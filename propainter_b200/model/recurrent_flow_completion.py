@@ -71,8 +71,8 @@ class RecurrentFlowCompleteNet(ParamNet):
         z = torch.cat([yp[0:t], yp[2:t + 2], yp[4:t + 4]], 1)                # dilation 2 taps
         return conv(z, self._wt(p + ".conv2.0"), act=act, slope=0.2)
 
-    def _up2_conv(self, key, x, act="none"):
-        return conv(up2(x), self._w2d(key + ".conv"), 1, 1, act=act, slope=0.2)
+    def _up2_conv(self, key, x, act="none", res=None):
+        return conv(up2(x), self._w2d(key + ".conv"), 1, 1, act=act, slope=0.2, res=res)
 
     def _propagate(self, x):
         """BidirectionalPropagation.forward :67-124.  x [t,128,h,w] channels_last -> same."""
@@ -122,22 +122,21 @@ class RecurrentFlowCompleteNet(ParamNet):
 
     def _forward_one(self, flows, masks):
         """one clip: flows [t,2,h,w], masks [t,1,h,w] -> [t,2,h,w]; captured as a CUDA graph per shape."""
-        if True:
-            x = torch.cat([flows, masks], 1)                                         # [t,3,h,w]
-            x = F.pad(x, (2, 2, 2, 2), mode="replicate").contiguous(memory_format=torch.channels_last)
-            x = conv(x, self._w2d("downsample.0"), 2, 0, act="leaky", slope=0.2)
-            e1 = self._p3d("encoder1.0", x, 1)
-            e1 = self._p3d("encoder1.2", e1, 2)
-            e2 = self._p3d("encoder2.0", e1, 1)
-            e2 = self._p3d("encoder2.2", e2, 2)
-            m = e2
-            for i, d in ((0, 3), (2, 2), (4, 1)):
-                m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
-            fpr = self._propagate(m)
-            d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky") + e1
-            d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
-            fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
-            return fl.contiguous()
+        x = torch.cat([flows, masks], 1)                                         # [t,3,h,w]
+        x = F.pad(x, (2, 2, 2, 2), mode="replicate").contiguous(memory_format=torch.channels_last)
+        x = conv(x, self._w2d("downsample.0"), 2, 0, act="leaky", slope=0.2)
+        e1 = self._p3d("encoder1.0", x, 1)
+        e1 = self._p3d("encoder1.2", e1, 2)
+        e2 = self._p3d("encoder2.0", e1, 1)
+        e2 = self._p3d("encoder2.2", e2, 2)
+        m = e2
+        for i, d in ((0, 3), (2, 2), (4, 1)):
+            m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
+        fpr = self._propagate(m)
+        d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
+        d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
+        fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
+        return fl.contiguous()
 
     @torch.no_grad()
     def forward_bidirect_flow(self, masked_flows_bi, masks):
