@@ -75,14 +75,15 @@ class TransformerExec:
         """feat [t,c,h,w] channels_last -> tokens [t,fh,fw,hidden] pixel-major (SoftSplit.forward :19-31)."""
         return as_pm(conv(feat, self._ss(), ST, PD))
 
-    def soft_comp(self, tokens, hw):
-        """tokens [t,fh,fw,hidden] -> [t,c,h,w] (SoftComp.forward :49-61)."""
+    def soft_comp(self, tokens, hw, res=None):
+        """tokens [t,fh,fw,hidden] -> [t,c,h,w] (SoftComp.forward :49-61); `res` = skip added in the last conv's epilogue."""
         fh, fw = tokens.shape[1:3]
         op = (hw[0] + 2 - 3 * fh, hw[1] + 2 - 3 * fw)
         y = F.conv_transpose2d(as_nchw(tokens), self._sc(), None, stride=ST, padding=PD, output_padding=op)
         y = y + self._sc_bias_map(tuple(hw))
         P = self.net.P
-        return conv(y, self.net.packed("scbc", lambda: (cl(P["sc.bias_conv.weight"]), P["sc.bias_conv.bias"].contiguous())), 1, 1)
+        return conv(y, self.net.packed("scbc", lambda: (cl(P["sc.bias_conv.weight"]), P["sc.bias_conv.bias"].contiguous())), 1, 1,
+                    res=res)
 
     # ------------------------------------------------------------------ transformer
     def run(self, tokens, hw, flags, t_dilation=2):

@@ -214,5 +214,5 @@ class InpaintGenerator(ParamNet):
         enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
         tok = self.tx.soft_split(enc2)
         tok = self.tx.run(tok, (h, w), flags, t_dilation)
-        enc3 = enc2 + self.tx.soft_comp(tok, (h, w))
+        enc3 = self.tx.soft_comp(tok, (h, w), res=enc2)                          # trans_feat + enc_feat (:365-366)
         return torch.tanh(self._decoder(enc3[:lt])).contiguous()
