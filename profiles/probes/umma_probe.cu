@@ -3,6 +3,12 @@
 // variant 0: A, B both K-major SWIZZLE_128B in shared memory (Q.K^T shape)
 // variant 1/2: B MN-major SWIZZLE_128B (V of P.V: rows = k, n contiguous), two LBO/SBO conventions
 // variant 3/4: like 0 / 1 but A comes from TMEM (written with tcgen05.st) -- P of P.V
+// variant 5/6: B MN-major in the SWIZZLE_128B_BASE32B layout (layout type 1) with A from smem / TMEM.  CUTLASS
+//              (cutlass/gemm/collective/builders/sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only
+//              available smem layout") explains why variants 1/2/4 return zeros: 32-bit MN-major operands need the
+//              32-byte-base swizzle  Swizzle<2,5,2>: atom = 4 k-rows x 128 B, 32-byte granule g of row r stored at g ^ (r & 3);
+//              canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp:238-268).
+//              NOT YET RUN ON HARDWARE (written at the end of round 1 with no GPU minutes left).
 // Each run prints max |D - ref| (fp32 host reference; TF32 inputs => ~1e-2 abs at these magnitudes).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_probe umma_probe.cu
 #include <cuda_runtime.h>
@@ -28,13 +34,18 @@ __device__ __forceinline__ uint32_t off_mnmajor(int k, int n, int nblocks) {
   int kg = k >> 3, kr = k & 7, nb = n >> 5, nn = n & 31, c = nn >> 2, w = nn & 3;
   return (uint32_t)((kg * nblocks + nb) * 1024 + kr * 128 + ((c ^ kr) << 4) + w * 4);
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major SWIZZLE_128B_BASE32B for B[k][n]: n-block (32 n = 128 B) major, then k rows of 128 B; 4-row swizzle atoms
+__device__ __forceinline__ uint32_t off_mn32(int k, int n, int krows) {
+  int nb = n >> 5, nn = n & 31, g = nn >> 3, w = nn & 7;
+  return (uint32_t)(nb * krows * 128 + k * 128 + ((g ^ (k & 3)) << 5) + w * 4);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;          // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;     // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -45,12 +56,13 @@ __global__ void __launch_bounds__(128) probe(const float* A, const float* B, flo
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool b_mn = (variant == 1 || variant == 2 || variant == 4);
-  const bool a_tmem = (variant == 3 || variant == 4);
+  const bool b_mn32 = (variant == 5 || variant == 6);
+  const bool b_mn = (variant == 1 || variant == 2 || variant == 4) || b_mn32;
+  const bool a_tmem = (variant == 3 || variant == 4 || variant == 6);
   for (int i = tid; i < M_ * K_; i += 128) { int m = i / K_, k = i % K_; *(float*)(sA + off_kmajor(m, k, M_)) = A[i]; }
   for (int i = tid; i < N_ * K_; i += 128) {
     int n = i / K_, k = i % K_;
-    uint32_t o = b_mn ? off_mnmajor(k, n, N_ / 32) : off_kmajor(n, k, N_);
+    uint32_t o = b_mn32 ? off_mn32(k, n, K_) : b_mn ? off_mnmajor(k, n, N_ / 32) : off_kmajor(n, k, N_);
     *(float*)(sB + o) = B[i];
   }
   if (warp == 0) {
@@ -89,7 +101,9 @@ __global__ void __launch_bounds__(128) probe(const float* A, const float* B, flo
       const uint64_t adesc = make_desc(sm(sA) + kb * (M_ * 128) + k8 * 32, 16, 1024);
       uint64_t bdesc;
       if (!b_mn) bdesc = make_desc(sm(sB) + kb * (N_ * 128) + k8 * 32, 16, 1024);
-      else {
+      else if (b_mn32) {                                             // 8 k-rows per MMA = 1024 B; LBO = n-block stride, SBO = 4-row group
+        bdesc = make_desc(sm(sB) + ks * 1024, K_ * 128, 512, 1);
+      } else {
         const uint32_t kstep = (N_ / 32) * 1024;                     // one 8-row k-group of atoms
         bdesc = (variant == 2) ? make_desc(sm(sB) + ks * kstep, kstep, 1024) : make_desc(sm(sB) + ks * kstep, 1024, kstep);
       }

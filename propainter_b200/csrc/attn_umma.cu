@@ -20,6 +20,13 @@
 #include "pp_mma.cuh"
 #include "../../include/propainter_b200.h"
 
+// UA_V_MN = 1: V tiles stay row-major (MN-major B operand in the SWIZZLE_128B_BASE32B layout, the only MN-major layout
+// tcgen05 accepts for 32-bit operands -- profiles/probes/umma_probe.cu variants 5/6), copied by cp.async like K: no
+// staging buffer, no transposing pass.  V then reaches the tensor core un-rounded (hardware truncation to TF32).
+// Default 0 until the probe has been run on hardware (written with no GPU minutes left in round 1).
+#ifndef UA_V_MN
+#define UA_V_MN 0
+#endif
 #define UA_BM 128
 #define UA_BN 64
 #define UA_THREADS 416                             // 4 softmax + 8 producer (two groups on alternate tiles) + 1 MMA warp
@@ -64,6 +71,17 @@ __device__ __forceinline__ void ua_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t ua_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_128B_BASE32B descriptor for the row-major V tile: LBO = stride between 32-dim blocks (UA_BN rows x 128 B),
+// SBO = 512 B between 4-row swizzle atoms, layout type 1
+__device__ __forceinline__ uint64_t ua_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((UA_BN * 128) >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of the 16-byte chunk c4 (dims 4*c4..) of key row `key` in that tile: 32-byte granule g stored at g ^ (key & 3)
+__device__ __forceinline__ uint32_t ua_off_mn(int key, int c4) {
+  const int nb = c4 >> 3, c8 = c4 & 7;
+  return (uint32_t)(nb * (UA_BN * 128) + key * 128 + ((((c8 >> 1) ^ (key & 3))) << 5) + (c8 & 1) * 16);
 }
 // byte offset of element (row, k) in a K-major SW128 tile with `rows` rows: k-block (32 floats) major, 8-row groups of 1 KB
 __device__ __forceinline__ uint32_t ua_off(int row, int k, int rows) {
@@ -166,7 +184,11 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
         const int kk = (ptid >> 5) + 4 * i, c4 = ptid & 31;
         const float* src = kp[kk];
         uint8_t* dk = sK + ua_off(kk, c4 * 4, UA_BN);
+#if UA_V_MN
+        float* dv = reinterpret_cast<float*>(sV + ua_off_mn(kk, c4));
+#else
         float* dv = stg + kk * UA_LDSTG + c4 * 4;
+#endif
         if (src) { pp_cp_async16(dk, src + c4 * 4); pp_cp_async16(dv, src + p.C + c4 * 4); }
         else {
           *reinterpret_cast<float4*>(dk) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -175,6 +197,7 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       }
       pp_cp_async_commit();
       pp_cp_async_wait<0>();
+#if !UA_V_MN
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // every thread's copies have landed
       else asm volatile("bar.sync 2, 128;" ::: "memory");
       // V^T: thread <-> (key, half of the head dims).  LDS.128 by key is conflict-free (row stride 132 floats); for a
@@ -192,6 +215,7 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
           *reinterpret_cast<uint32_t*>(sV + ua_off(d + 3, key, 128)) = pp_tf32(v.w);
         }
       }
+#endif
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
       ua_bar_arrive(bar(s));
     }
@@ -199,7 +223,8 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
     // ================================================= MMA issuer (one elected thread)
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
-      const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24) |
+                               (UA_V_MN ? (1u << 16) : 0u);               // bit 16: B operand MN-major
       auto issue_s = [&](int j) {                                        // caller has observed kv_full for tile j
         const int sb = j & 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -215,8 +240,12 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
         const uint32_t vaddr = ua_smem(base + st * UA_STAGE_BYTES + UA_K_BYTES);
 #pragma unroll
         for (int ks = 0; ks < UA_BN / 8; ++ks)                            // 64 keys = 2 k-blocks x 4 k-steps
+#if UA_V_MN
+          ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, ua_desc_mn(vaddr + ks * 1024), idesc_o, (j > 0 || ks > 0));   // 8 key rows x 128 B
+#else
           ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, ua_desc(vaddr + (ks >> 2) * (128 * 128) + (ks & 3) * 32), idesc_o,
                     (j > 0 || ks > 0));
+#endif
         ua_commit(bar(3 + st));                                          // stage may be refilled
         ua_commit(bar(10));                                              // O holds tiles 0..j
       };
