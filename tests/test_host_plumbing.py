@@ -102,3 +102,16 @@ def test_half_storage_is_accepted(emu):
     comb = net.combine_flow((flows[0].half(), flows[1].half()), out, masks.half())
     assert comb[0].dtype == torch.float16
     net.float().load_state_dict(sd32, strict=True)
+
+
+@pytest.mark.parametrize("T,kw", [(2, {}), (3, {}), (5, dict(neighbor_length=20, ref_stride=20)), (7, dict(neighbor_length=2, ref_stride=3))])
+def test_pipeline_edge_lengths(emu, T, kw):
+    """Shortest clips (one flow), window / reference strides larger than the clip, and a stride-3 reference schedule:
+    the driver's window plan (inference_propainter.py:159-173, :417-452) must keep matching the oracle's."""
+    from propainter_b200 import synth
+    from propainter_b200.inference_propainter import InferenceConfig, ProPainterPipeline
+    u8, fm, md = synth.make_clip(T, 128, 128, mask="ellipse", seed=0)
+    pipe = ProPainterPipeline(device="cpu")
+    comp = pipe(torch.from_numpy(u8), fm, md, InferenceConfig(raft_iter=1, **kw))
+    ref = pipeline_ref.run_pipeline(pipe.state_dicts(), u8, fm, md, raft_iter=1, **kw)
+    assert comp.shape == (T, 128, 128, 3) and ops_ref.psnr_u8(comp.numpy(), ref) > 60.0
