@@ -8,7 +8,7 @@
 //              available smem layout") explains why variants 1/2/4 return zeros: 32-bit MN-major operands need the
 //              32-byte-base swizzle  Swizzle<2,5,2>: atom = 4 k-rows x 128 B, 32-byte granule g of row r stored at g ^ (r & 3);
 //              canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp:238-268).
-//              NOT YET RUN ON HARDWARE (written at the end of round 1 with no GPU minutes left).
+//              Verified on B200: variants 5 and 6 reproduce variant 3's result (profiles/r1_attn_vmn_probe.log).
 // Each run prints max |D - ref| (fp32 host reference; TF32 inputs => ~1e-2 abs at these magnitudes).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_probe umma_probe.cu
 #include <cuda_runtime.h>

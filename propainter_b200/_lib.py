@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpropainter_b200.so")
+# PROPAINTER_B200_LIB selects another build of the same ABI (e.g. an experiment compiled with different -D flags)
+LIB_PATH = os.environ.get("PROPAINTER_B200_LIB") or os.path.join(_HERE, "libpropainter_b200.so")
 
 c_void_p, c_int, c_long, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
 
