@@ -101,6 +101,42 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().pp_img_prop_scan_workspace_bytes(3, 4, 5) == 3 * 4 * 4 * 5 * 4
 
 
+def test_ctypes_table_matches_header_prototypes():
+    """Every prototype of include/propainter_b200.h, parameter by parameter, against the argtypes the Python side binds
+    (`_lib.SIGNATURES`): a transposed or missing argument would otherwise only show up as garbage on the GPU.  The .cu
+    files include the same header, so the compiler already ties the prototypes to the definitions."""
+    from propainter_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "propainter_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"\b([A-Za-z_][\w \*]*?)\b(pp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def ctype(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            for struct in ("PPAttnParams", "PPWindowIds"):
+                if struct in decl:
+                    return ctypes.POINTER(getattr(_lib, struct))
+            return ctypes.c_char_p if decl.replace("const", "").strip().startswith("char") and "(" not in decl and decl.count(" ") <= 1 else ctypes.c_void_p
+        base = re.sub(r"\b(const|unsigned)\b", "", decl).split()
+        kind = base[0]
+        return {"int": ctypes.c_int, "long": ctypes.c_long, "float": ctypes.c_float, "size_t": ctypes.c_size_t,
+                "cudaStream_t": ctypes.c_void_p, "PPLevels": None}[kind]
+
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        want = [] if params.strip() in ("", "void") else [ctype(a) for a in params.split(",")]
+        assert len(want) == len(args), (name, params)
+        for i, (w, a) in enumerate(zip(want, args)):
+            if w is ctypes.c_char_p:
+                w = ctypes.c_void_p
+            assert w is a or (w is ctypes.c_void_p and a is ctypes.c_void_p), (name, i, params.split(",")[i].strip(), a)
+        ret = ret.strip()
+        want_res = ctypes.c_char_p if "char" in ret else ctype(ret + " x")
+        assert want_res is res, (name, ret, res)
+
+
 def test_ops_refuse_cpu_tensors():
     """No CPU fallback: wrappers raise instead of computing on the host."""
     from propainter_b200 import ops
