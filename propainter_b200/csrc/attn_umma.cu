@@ -34,11 +34,18 @@
 #define UA_K_BYTES (UA_BN * 128 * 4)               // 32 KB: 4 k-blocks of [64 rows x 128 B]
 #define UA_V_BYTES (128 * UA_BN * 4)               // 32 KB: 2 k-blocks of [128 rows x 128 B]  (V^T: rows = head dim)
 #define UA_STAGE_BYTES (UA_K_BYTES + UA_V_BYTES)
-#define UA_STAGES 2                                // one K/V stage per producer group
 #define UA_LDSTG 132                               // V staging rows: 128 floats + 4 pad (conflict-free LDS.128 by key)
+#ifndef UA_STAGES
+#define UA_STAGES 2                                // K/V stages (one per producer group); 3 fits only with UA_V_MN=1 (untested)
+#endif
+#if UA_V_MN
+#define UA_STG_BYTES 0                             // no V staging buffers
+#else
 #define UA_STG_BYTES (UA_BN * UA_LDSTG * 4)
+#endif
 #define UA_TAIL_BYTES 3072                          // barriers, TMEM base (+128), token table (<= 224 ints at +256), key row pointers (+1152)
-#define UA_SMEM_BYTES (UA_STAGES * (UA_STAGE_BYTES + UA_STG_BYTES) + UA_TAIL_BYTES + 1024)
+#define UA_SMEM_BYTES (UA_STAGES * UA_STAGE_BYTES + 2 * UA_STG_BYTES + UA_TAIL_BYTES + 1024)   // staging: one per producer group
+static_assert(UA_STAGES >= 2 && UA_STAGES <= 3 && UA_SMEM_BYTES <= 227 * 1024, "stage count does not fit the 227 KB of shared memory");
 
 __device__ __forceinline__ uint32_t ua_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ua_bar_init(uint32_t bar, int count) {
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
   // SWIZZLE_128B tiles need 1 KB alignment; the pad is applied as an offset so the pointer stays in the shared window
   uint8_t* base = ua_raw + ((1024u - (ua_smem(ua_raw) & 1023u)) & 1023u);
   uint8_t* stg_base = base + UA_STAGES * UA_STAGE_BYTES;             // per-group V staging (row-major, padded)
-  uint8_t* tail = stg_base + UA_STAGES * UA_STG_BYTES;
+  uint8_t* tail = stg_base + 2 * UA_STG_BYTES;
   // barriers: 0-2 kv_full[3]  3-5 kv_empty[3]  6,7 s_full[2]  8,9 p_full[2]  10 pv_done  11 q_ready
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tail);
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(tail + 128);
