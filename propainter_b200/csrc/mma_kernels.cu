@@ -486,6 +486,142 @@ __global__ void __launch_bounds__(NWARPS * 32) k_sparse_attn(PPAttnParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// AT_UNMASKED_LOOP = 1 (experiment, default 0): unmasked windows with one CTA walking several frames of its
+// (window, head).  The one-frame CTAs above are a serial load -> compute -> store chain (11 % warps active, 52 us per
+// C2 layer call, profiles/r1_ncu_final_kernels.csv); here the K/V rows of frame f+1 arrive by cp.async in the other
+// stage while frame f is computed, stages hold 48 instead of 64 key rows (2 CTAs/SM with both stages), and the Q
+// fragments come straight from global memory.  Same fragment maps and summation order as k_sparse_attn<false,4>, so
+// the results must be bit-identical.  Not yet run on hardware: build a second library with -DAT_UNMASKED_LOOP=1 and run
+// tests/test_gpu_ops.py::test_sparse_window_attention + profiles/attn_vmn_check.py with PROPAINTER_B200_LIB pointing at it.
+#ifndef AT_UNMASKED_LOOP
+#define AT_UNMASKED_LOOP 0
+#endif
+#define AU_KEYS 48
+#define AU_STAGE (AU_KEYS * AT_LDK + AU_KEYS * AT_LDV)
+__global__ void __launch_bounds__(128, 2) k_attn_unmasked_frames(PPAttnParams p, int fpc) {
+  extern __shared__ __align__(16) float smem[];
+  const int win = blockIdx.z, head = blockIdx.y;
+  if (p.flags[win] != 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int* ktab = p.key_tok + (long)win * p.NKO;
+  const int hoff = head * 128, WN = p.WN;
+  const int f0 = blockIdx.x * fpc, f1 = min(p.t, f0 + fpc);
+  if (f0 >= f1) return;
+  auto Kst = [&](int st) { return smem + st * AU_STAGE; };
+  auto Vst = [&](int st) { return smem + st * AU_STAGE + AU_KEYS * AT_LDK; };
+  auto gather = [&](int f, int st) {
+    float* Ks = Kst(st); float* Vs = Vst(st);
+    for (int idx = tid; idx < WN * 32; idx += 128) {
+      const int key = idx >> 5, c4 = idx & 31;
+      const float* src = p.qkv + ((long)f * p.NT + ktab[key]) * p.ld_qkv + p.C + hoff;
+      pp_cp_async16(Ks + key * AT_LDK + c4 * 4, src + c4 * 4);
+      pp_cp_async16(Vs + key * AT_LDV + c4 * 4, src + p.C + c4 * 4);
+    }
+    pp_cp_async_commit();
+  };
+  // pad key rows [WN, 48) of both stages: zero once (their P is 0, but 0 * stale-NaN would poison the accumulators)
+  for (int idx = tid; idx < 2 * (AU_KEYS - WN) * 32; idx += 128) {
+    const int st = idx / ((AU_KEYS - WN) * 32), r = idx - st * (AU_KEYS - WN) * 32, key = WN + (r >> 5), c4 = r & 31;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Kst(st) + key * AT_LDK + c4 * 4) = z;
+    *reinterpret_cast<float4*>(Vst(st) + key * AT_LDV + c4 * 4) = z;
+  }
+  gather(f0, 0);
+  const int ra = warp * 16 + g, rb = ra + 8;
+  const int ta = ra < WN ? ktab[ra] : -1, tb = rb < WN ? ktab[rb] : -1;
+  for (int f = f0; f < f1; ++f) {
+    const int cur = (f - f0) & 1;
+    // ---- Q fragments of frame f straight from global (rows ra / rb of this warp), scaled into the log2 domain
+    uint32_t qa[16][4];
+    {
+      const float* r0 = p.qkv + ((long)f * p.NT + (ta >= 0 ? ta : 0)) * p.ld_qkv + hoff;
+      const float* r1 = p.qkv + ((long)f * p.NT + (tb >= 0 ? tb : 0)) * p.ld_qkv + hoff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (ta >= 0) lo = *reinterpret_cast<const float4*>(r0 + 16 * j + 4 * t);
+        if (tb >= 0) hi = *reinterpret_cast<const float4*>(r1 + 16 * j + 4 * t);
+        lo.x *= p.scale_log2; lo.y *= p.scale_log2; lo.z *= p.scale_log2; lo.w *= p.scale_log2;
+        hi.x *= p.scale_log2; hi.y *= p.scale_log2; hi.z *= p.scale_log2; hi.w *= p.scale_log2;
+        qa[2 * j][0] = pp_tf32(lo.x); qa[2 * j][1] = pp_tf32(hi.x); qa[2 * j][2] = pp_tf32(lo.y); qa[2 * j][3] = pp_tf32(hi.y);
+        qa[2 * j + 1][0] = pp_tf32(lo.z); qa[2 * j + 1][1] = pp_tf32(hi.z); qa[2 * j + 1][2] = pp_tf32(lo.w); qa[2 * j + 1][3] = pp_tf32(hi.w);
+      }
+    }
+    pp_cp_async_wait<0>();
+    __syncthreads();                          // frame f landed; every warp is done with the other stage
+    if (f + 1 < f1) gather(f + 1, cur ^ 1);
+    if (warp * 16 >= WN) continue;            // this warp's 16 query rows are all padding (no barrier below this point)
+    const float* Ks = Kst(cur); const float* Vs = Vst(cur);
+    // ---- S = Q K^T, 6 n-tiles of 8 keys
+    float s[6][4];
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const float* kr = Ks + (nt * 8 + g) * AT_LDK + 4 * t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 kv = *reinterpret_cast<const float4*>(kr + 16 * j);
+        uint32_t b[2];
+        b[0] = pp_tf32(kv.x); b[1] = pp_tf32(kv.y); pp_mma_tf32(s[nt], qa[2 * j], b);
+        b[0] = pp_tf32(kv.z); b[1] = pp_tf32(kv.w); pp_mma_tf32(s[nt], qa[2 * j + 1], b);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      const int j = nt * 8 + 2 * t;
+      if (j >= WN) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (j + 1 >= WN) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mx0); s[nt][1] = exp2f(s[nt][1] - mx0);
+      s[nt][2] = exp2f(s[nt][2] - mx1); s[nt][3] = exp2f(s[nt][3] - mx1);
+      l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
+    }
+    // ---- O = P V
+    float oacc[16][4];
+#pragma unroll
+    for (int a = 0; a < 16; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) oacc[a][b] = 0.f;
+#pragma unroll
+    for (int kg = 0; kg < 6; ++kg) {
+      const uint32_t a[4] = {pp_tf32(s[kg][0]), pp_tf32(s[kg][2]), pp_tf32(s[kg][1]), pp_tf32(s[kg][3])};
+      const float* v0 = Vs + (kg * 8 + 2 * t) * AT_LDV + 4 * g;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v0 + 32 * q);
+        const float4 x1 = *reinterpret_cast<const float4*>(v0 + AT_LDV + 32 * q);
+        uint32_t b[2];
+        b[0] = pp_tf32(x0.x); b[1] = pp_tf32(x1.x); pp_mma_tf32(oacc[4 * q + 0], a, b);
+        b[0] = pp_tf32(x0.y); b[1] = pp_tf32(x1.y); pp_mma_tf32(oacc[4 * q + 1], a, b);
+        b[0] = pp_tf32(x0.z); b[1] = pp_tf32(x1.z); pp_mma_tf32(oacc[4 * q + 2], a, b);
+        b[0] = pp_tf32(x0.w); b[1] = pp_tf32(x1.w); pp_mma_tf32(oacc[4 * q + 3], a, b);
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    float* oa = ta >= 0 ? p.out + ((long)f * p.NT + ta) * p.ld_out + hoff : nullptr;
+    float* ob = tb >= 0 ? p.out + ((long)f * p.NT + tb) * p.ld_out + hoff : nullptr;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int n = 32 * q + 4 * (2 * t + c);
+        if (oa) *reinterpret_cast<float4*>(oa + n) = make_float4(oacc[4 * q][c] * inv0, oacc[4 * q + 1][c] * inv0, oacc[4 * q + 2][c] * inv0, oacc[4 * q + 3][c] * inv0);
+        if (ob) *reinterpret_cast<float4*>(ob + n) = make_float4(oacc[4 * q][c + 2] * inv1, oacc[4 * q + 1][c + 2] * inv1, oacc[4 * q + 2][c + 2] * inv1, oacc[4 * q + 3][c + 2] * inv1);
+      }
+  }
+}
+
 int pp_launch_sparse_attn_umma(const PPAttnParams& p, int n_windows, cudaStream_t stream);   // attn_umma.cu
 
 static int pp_attn_check(const PPAttnParams& p) {
@@ -494,6 +630,19 @@ static int pp_attn_check(const PPAttnParams& p) {
   return PP_OK;
 }
 static int pp_attn_unmasked(const PPAttnParams& p, int n_windows, cudaStream_t stream) {
+#if AT_UNMASKED_LOOP
+  if (p.WN <= AU_KEYS && p.WN >= 1) {
+    const int smem2 = 2 * AU_STAGE * (int)sizeof(float);
+    if (cudaFuncSetAttribute(k_attn_unmasked_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess)
+      return PP_ERR_LAUNCH;
+    int fpc = (p.t * (p.C / 128) * n_windows + 295) / 296;         // ~one wave of 2 CTAs/SM over all (frame, head, window) units
+    fpc = fpc < 1 ? 1 : (fpc > 8 ? 8 : fpc);
+    dim3 gl((p.t + fpc - 1) / fpc, p.C / 128, n_windows);
+    k_attn_unmasked_frames<<<gl, 128, smem2, stream>>>(p, fpc);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
+#endif
   const int smem1 = AT_STAGE * (int)sizeof(float);
   if (cudaFuncSetAttribute(k_sparse_attn<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1) != cudaSuccess)
     return PP_ERR_LAUNCH;
