@@ -66,7 +66,14 @@ int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int ld_prop, c
 size_t pp_deform_align_workspace_bytes(int H, int W);   /* decoded tap records + split-K partial sums */
 int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
                     const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin, int Cout,
-                    void* workspace, size_t ws_bytes, cudaStream_t stream);   /* o_bias: bias of conv_offset.6 if not yet added, else NULL */
+                    void* workspace, size_t ws_bytes, cudaStream_t stream);
+/* The same op on a batch of n maps: x [n][H][W][ld_x], o [n][H][W][ld_o], flow [n][H][W][2] | NULL, out [n][H][W][ld_out]
+ * (the forward- and backward-flow nets of forward_bidirect_flow, model/recurrent_flow_completion.py:312-337, advance in
+ * lock step: one launch set serves both). */
+size_t pp_deform_align_batched_workspace_bytes(int n, int H, int W);
+int pp_deform_align_batched(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
+                            float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int n, int H, int W,
+                            int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream);   /* o_bias: bias of conv_offset.6 if not yet added, else NULL */
 
 /* ---- generator glue ------------------------------------------------------------------------- */
 /* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar

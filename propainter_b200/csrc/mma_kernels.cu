@@ -127,6 +127,23 @@ __global__ void __launch_bounds__(256) k_deform_taps(const float* __restrict__ o
   taps[i] = make_float4((float)(y - 1 + k / 3) + oy, (float)(x - 1 + k % 3) + ox, 1.0f / (1.0f + expf(-ml)), 0.f);
 }
 
+// same for a batch of `nimg` maps stacked along the pixel index ([n][H][W] pixel-major): sampling coordinates are per image
+__global__ void __launch_bounds__(256) k_deform_taps_batched(const float* __restrict__ o, int ld_o, const float* __restrict__ obias,
+    const float* __restrict__ flow, float max_res, float4* __restrict__ taps, int nimg, int H, int W) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // (pix*9 + k)*16 + g
+  const long HW = (long)H * W;
+  if (i >= nimg * HW * 144) return;
+  const int g = (int)(i & 15); const long r = i >> 4; const int k = (int)(r % 9); const long pix = r / 9;
+  const long pim = pix % HW;
+  const int y = (int)(pim / W), x = (int)(pim - (long)y * W);
+  const float* op = o + pix * ld_o;
+  float oy = op[g * 18 + 2 * k], ox = op[g * 18 + 2 * k + 1], ml = op[288 + g * 9 + k];
+  if (obias) { oy += obias[g * 18 + 2 * k]; ox += obias[g * 18 + 2 * k + 1]; ml += obias[288 + g * 9 + k]; }
+  oy = max_res * tanhf(oy); ox = max_res * tanhf(ox);
+  if (flow) { oy += flow[2 * pix + 1]; ox += flow[2 * pix]; }
+  taps[i] = make_float4((float)(y - 1 + k / 3) + oy, (float)(x - 1 + k % 3) + ox, 1.0f / (1.0f + expf(-ml)), 0.f);
+}
+
 struct DARaw { float4 u[4], v[4]; float w[4]; };
 // issue the 8 corner loads of (tap position tp, 8 channels from c); corners with zero weight read a safe address
 __device__ __forceinline__ void da_issue(const float* __restrict__ x, int ld_x, const float4 tp, int H, int W, int c, bool valid,
@@ -153,111 +170,25 @@ __device__ __forceinline__ void da_combine(const DARaw& r, float4& s0, float4& s
   }
 }
 
-__global__ void __launch_bounds__(128) k_deform_align(const float* __restrict__ x, int ld_x, const float4* __restrict__ taps,
-    const float* __restrict__ Wp, const float* __restrict__ bias, float* __restrict__ out, int ld_out, int H, int W, int Cin,
-    float* __restrict__ part) {
-  // gridDim.y > 1: split-K over the 9*Cin/32 K-steps -- CTA row y accumulates its share into part[y][pix][128]
-  // (reduced + biased by k_deform_reduce); a 6480- or 1620-pixel map alone gives only 203 / 51 CTAs.
-  // Software pipeline per K-step `it`: the tap record of step it+2 and the 8 corner loads of step it+1 are issued
-  // BEFORE the MMAs of step it and consumed after them, and the weight slab of it+1 arrives by cp.async meanwhile.
-  __shared__ __align__(16) float As[2][32][DA_LDA];
-  __shared__ __align__(16) float Bs[2][32][DA_LDB];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;
-  const int px_l = tid >> 2, cseg = tid & 3;
-  const long npix = (long)H * W;
-  const long pix = (long)blockIdx.x * 32 + px_l;
-  const bool valid = pix < npix;
-  const long pixc = valid ? pix : 0;
-  const int cpg = Cin / 16, cblocks = Cin / 32, nit_all = 9 * cblocks;
-  const int it0 = (int)((long)nit_all * blockIdx.y / gridDim.y), it1 = (int)((long)nit_all * (blockIdx.y + 1) / gridDim.y);
-  float acc[8][4];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-
-  auto load_b = [&](int it, int buf) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      int idx = tid + 128 * r, row = idx >> 5, c4 = idx & 31;
-      pp_cp_async16(&Bs[buf][row][c4 * 4], Wp + ((long)it * 32 + row) * 128 + c4 * 4);   // rows of Wp are (k*Cin + c): it*32 == k*Cin + c0
-    }
-    pp_cp_async_commit();
-  };
-  auto chan = [&](int it) { const int k = it / cblocks; return (it - k * cblocks) * 32 + cseg * 8; };
-  auto tap_of = [&](int it) { const int k = it / cblocks; return taps[(pixc * 9 + k) * 16 + chan(it) / cpg]; };
-  auto store_a = [&](const DARaw& r, int buf) {
-    float4 s0, s1;
-    da_combine(r, s0, s1);
-    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8]) = s0;
-    *reinterpret_cast<float4*>(&As[buf][px_l][cseg * 8 + 4]) = s1;
-  };
-
-  DARaw raw;
-  load_b(it0, 0);
-  da_issue(x, ld_x, tap_of(it0), H, W, chan(it0), valid, raw);
-  float4 tp_next = it0 + 1 < it1 ? tap_of(it0 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-  store_a(raw, 0);
-  pp_cp_async_wait<0>();
-  __syncthreads();
-
-  for (int it = it0; it < it1; ++it) {
-    const int cur = (it - it0) & 1, nxt = cur ^ 1;
-    const bool more = it + 1 < it1;
-    float4 tp_next2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (more) {
-      load_b(it + 1, nxt);
-      if (it + 2 < it1) tp_next2 = tap_of(it + 2);
-      da_issue(x, ld_x, tp_next, H, W, chan(it + 1), valid, raw);
-    }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      uint32_t a[4];
-      const int r0 = wm * 16 + g;
-      const float2 alo = *reinterpret_cast<const float2*>(&As[cur][r0][ks * 8 + 2 * t]);
-      const float2 ahi = *reinterpret_cast<const float2*>(&As[cur][r0 + 8][ks * 8 + 2 * t]);
-      a[0] = pp_tf32(alo.x); a[1] = pp_tf32(ahi.x); a[2] = pp_tf32(alo.y); a[3] = pp_tf32(ahi.y);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][ks * 8 + 2 * t][wn * 64 + 32 * q + 4 * g]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][ks * 8 + 2 * t + 1][wn * 64 + 32 * q + 4 * g]);
-        uint32_t b[2];
-        b[0] = pp_tf32(b0.x); b[1] = pp_tf32(b1.x); pp_mma_tf32(acc[4 * q + 0], a, b);
-        b[0] = pp_tf32(b0.y); b[1] = pp_tf32(b1.y); pp_mma_tf32(acc[4 * q + 1], a, b);
-        b[0] = pp_tf32(b0.z); b[1] = pp_tf32(b1.z); pp_mma_tf32(acc[4 * q + 2], a, b);
-        b[0] = pp_tf32(b0.w); b[1] = pp_tf32(b1.w); pp_mma_tf32(acc[4 * q + 3], a, b);
-      }
-    }
-    if (more) {
-      store_a(raw, nxt);
-      pp_cp_async_wait<0>();
-    }
-    tp_next = tp_next2;
-    __syncthreads();
-  }
-  // epilogue: tile 4q+j, C-fragment column 2t+c  <->  physical column wn*64 + 32q + 4(2t+c) + j
-  const long p0 = (long)blockIdx.x * 32 + wm * 16 + g, p1 = p0 + 8;
-  const bool split = gridDim.y > 1;
-  float* dst = split ? part + (long)blockIdx.y * npix * 128 : out;
-  const int ldd = split ? 128 : ld_out;
-#pragma unroll
-  for (int q = 0; q < 2; ++q)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int n = wn * 64 + 32 * q + 4 * (2 * t + c);
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!split) bv = *reinterpret_cast<const float4*>(bias + n);
-      if (p0 < npix) {
-        float4 v = make_float4(acc[4 * q][c] + bv.x, acc[4 * q + 1][c] + bv.y, acc[4 * q + 2][c] + bv.z, acc[4 * q + 3][c] + bv.w);
-        *reinterpret_cast<float4*>(dst + p0 * ldd + n) = v;
-      }
-      if (p1 < npix) {
-        float4 v = make_float4(acc[4 * q][c + 2] + bv.x, acc[4 * q + 1][c + 2] + bv.y, acc[4 * q + 2][c + 2] + bv.z, acc[4 * q + 3][c + 2] + bv.w);
-        *reinterpret_cast<float4*>(dst + p1 * ldd + n) = v;
-      }
-    }
-}
+#define DA_NAME k_deform_align
+#define DA_EXTRA_PARAMS
+#define DA_NPIX ((long)H * W)
+#define DA_REBASE
+#include "deform_align_body.inc"
+#undef DA_NAME
+#undef DA_EXTRA_PARAMS
+#undef DA_NPIX
+#undef DA_REBASE
+// n maps stacked along the pixel index ([n][H][W] pixel-major): every pixel samples from its own map only
+#define DA_NAME k_deform_align_batched
+#define DA_EXTRA_PARAMS , int nimg
+#define DA_NPIX ((long)nimg * H * W)
+#define DA_REBASE x += (pixc / ((long)H * W)) * ((long)H * W) * ld_x;
+#include "deform_align_body.inc"
+#undef DA_NAME
+#undef DA_EXTRA_PARAMS
+#undef DA_NPIX
+#undef DA_REBASE
 
 __global__ void __launch_bounds__(256) k_deform_reduce(const float* __restrict__ part, const float* __restrict__ bias,
                                                        float* __restrict__ out, int ld_out, long npix, int splits) {
@@ -306,6 +237,29 @@ extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_
   k_deform_taps<<<(int)((npix * 144 + 255) / 256), 256, 0, stream>>>(o, ld_o, o_bias, flow, max_res, taps, H, W);
   dim3 grid((unsigned)((npix + 31) / 32), splits);
   k_deform_align<<<grid, 128, 0, stream>>>(x, ld_x, taps, w_packed, bias, out, ld_out, H, W, Cin, part);
+  if (splits > 1)
+    k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>(part, bias, out, ld_out, npix, splits);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// the same op on a batch of n maps ([n][H][W][ld] pixel-major; flow [n][H][W][2]): one launch set for all of them.  The
+// recurrent scans run on 1620- / 6480-pixel maps whose kernels fill a fraction of the GPU, so two independent scans
+// (the forward- and backward-flow nets of RecurrentFlowCompleteNet.forward_bidirect_flow) cost what one does.
+extern "C" size_t pp_deform_align_batched_workspace_bytes(int n, int H, int W) { return pp_deform_align_workspace_bytes(n * H, W); }
+extern "C" int pp_deform_align_batched(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
+                                       float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int n,
+                                       int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (Cout != 128 || Cin % 32 || (Cin / 16) % 8 || n < 1) return PP_ERR_SHAPE;
+  if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)x & 15)) return PP_ERR_ALIGN;
+  const long npix = (long)n * H * W;
+  const int splits = da_splits(npix, 9 * (Cin / 32));
+  if (ws_bytes < pp_deform_align_batched_workspace_bytes(n, H, W) || ((uintptr_t)workspace & 15)) return PP_ERR_WORKSPACE;
+  float4* taps = (float4*)workspace;
+  float* part = (float*)(taps + npix * 144);
+  k_deform_taps_batched<<<(int)((npix * 144 + 255) / 256), 256, 0, stream>>>(o, ld_o, o_bias, flow, max_res, taps, n, H, W);
+  dim3 grid((unsigned)((npix + 31) / 32), splits);
+  k_deform_align_batched<<<grid, 128, 0, stream>>>(x, ld_x, taps, w_packed, bias, out, ld_out, H, W, Cin, part, n);
   if (splits > 1)
     k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>(part, bias, out, ld_out, npix, splits);
   PP_LAUNCH_CHECK();

@@ -129,7 +129,20 @@ def prop_cond(cur, prop, fprop, fcheck, mcur, cond, bb, first):
 
 def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
     """x [H,W,Cin] view, o [H,W,>=432] view (raw conv_offset.6 output; its bias may be passed as o_bias instead of being
-    pre-added), flow [H,W,2]|None, out [H,W,128] view (all pixel-major)."""
+    pre-added), flow [H,W,2]|None, out [H,W,128] view (all pixel-major).  4-D tensors [n,H,W,.] run the batched entry."""
+    if x.dim() == 4:
+        n, H, W, Cin = x.shape
+        xp, ldx = _pm(x)
+        op, ldo = _pm(o)
+        outp, ldout = _pm(out)
+        L = _lib.lib()
+        ws_bytes = L.pp_deform_align_batched_workspace_bytes(n, H, W)
+        ws = torch.empty(max(ws_bytes // 4, 4), device=x.device, dtype=torch.float32)
+        check(L.pp_deform_align_batched(xp, ldx, op, ldo, _p(o_bias), _p(_dense(flow)) if flow is not None else None, float(max_res),
+                                        _p(_dense(w_packed)), _p(bias), outp, ldout, n, H, W, Cin, out.shape[-1], _p(ws), ws_bytes,
+                                        _stream()), "pp_deform_align_batched")
+        _count(3)
+        return out
     H, W, Cin = x.shape
     xp, ldx = _pm(x)
     op, ldo = _pm(o)

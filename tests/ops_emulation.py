@@ -69,6 +69,10 @@ def install(monkeypatch, hostsim):
         return ctypes.cast(t.data_ptr(), FP)
 
     def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
+        if x.dim() == 4:                                  # batched entry: independent maps
+            for i in range(x.shape[0]):
+                deform_align(x[i], o[i], None if flow is None else flow[i], max_res, w_packed, bias, out[i], o_bias)
+            return out
         H, W, Cin = x.shape
         if o_bias is not None:
             o = (o + o_bias).contiguous()

@@ -47,6 +47,24 @@ def test_flow_completion_plumbing(emu):
     assert rel_err(pred[0], ref[0]) < 1e-4 and rel_err(pred[1], ref[1]) < 1e-4, (rel_err(pred[0], ref[0]), rel_err(pred[1], ref[1]))
 
 
+def test_flow_completion_batched_directions(emu, monkeypatch):
+    """config.RFC_BATCHED: the forward- and backward-flow nets as one batch of two (clip-major stacking, per-clip temporal
+    taps in the P3D blocks, batched deform-align) must give what the two independent runs give."""
+    from propainter_b200 import config
+    from propainter_b200.model.recurrent_flow_completion import RecurrentFlowCompleteNet
+    net = RecurrentFlowCompleteNet(None, seed=2)
+    gen = torch.Generator().manual_seed(0)
+    flows = (torch.randn(1, 5, 2, 32, 48, generator=gen), torch.randn(1, 5, 2, 32, 48, generator=gen))
+    masks = torch.zeros(1, 6, 1, 32, 48)
+    masks[..., 8:24, 12:36] = 1
+    sep, _ = net.forward_bidirect_flow(flows, masks)
+    monkeypatch.setattr(config, "RFC_BATCHED", True)
+    bat, _ = net.forward_bidirect_flow(flows, masks)
+    ref = flowcomp_ref.forward_bidirect_flow(net.state_dict(), flows, masks)
+    for k in (0, 1):
+        assert rel_err(bat[k], ref[k]) < 1e-4 and rel_err(bat[k], sep[k]) < 1e-5, (rel_err(bat[k], ref[k]), rel_err(bat[k], sep[k]))
+
+
 @pytest.mark.parametrize("H,W,t,lt,alt", [(64, 96, 4, 3, False), (128, 128, 3, 2, False), (64, 64, 2, 1, False), (64, 96, 4, 3, True)])
 def test_generator_plumbing(emu, monkeypatch, H, W, t, lt, alt):
     from propainter_b200 import autotune
