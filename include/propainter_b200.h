@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 int pp_abi_version(void);
 const char* pp_error_string(int code);
 
@@ -74,6 +74,43 @@ size_t pp_deform_align_batched_workspace_bytes(int n, int H, int W);
 int pp_deform_align_batched(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
                             float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int n, int H, int W,
                             int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream);   /* o_bias: bias of conv_offset.6 if not yet added, else NULL */
+
+/* ---- tcgen05 convolution (conv_umma.cu) -------------------------------------------------------- */
+/* Stride-1 "same" KHxKW convolution + the epilogue that follows it in the reference, as one kernel:
+ *   out = post_relu?( act( conv(cat(seg...), W) + bias + pre ) + res )        [optionally rounded to TF32 on store]
+ * Replaces F.conv2d / nn.Conv2d (cuDNN) + bias + nn.LeakyReLU/ReLU + residual add + torch.cat of the recurrent
+ * propagation steps: model/propainter.py:42-50 (conv_offset), :86-96 (backbone / fuse), :146-176 (step);
+ * model/recurrent_flow_completion.py:17-29, :60-66, :96-110; RAFT/update.py:33-60,79-97 (same op, 1x5 / 5x1 / 3x3).
+ * With KH = KW = 1 over the columns written by pp_deform_gather it is the GEMM of torchvision.ops.deform_conv2d
+ * (model/propainter.py:67-69, model/recurrent_flow_completion.py:42-44).
+ * seg[i]: pixel-major input maps [n][H][W][ld] (C channels used, any C >= 1; ld % 4 == 0) concatenated along channels.
+ * w_packed: [Cout][K], K = KH*KW*sum_i roundup32(C_i); inside segment i, 32-channel block b (global block index blk):
+ *   k = ((blk*KH + dy)*KW + dx)*32 + c   (c = channel - 32*b; padded channels hold zeros).  TF32 products, fp32 accumulate.
+ * bias [Cout] | NULL; pre (pre-activation addend) / res (post-activation residual): pixel-major [n*H*W][ld] | NULL.
+ * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh.  Cout % 4 == 0.  bn / tile_w: 0 = choose (see _plan). */
+#define PP_CONV_MAX_SEG 4
+typedef struct PPConvSeg { const float* x; int ld; int C; } PPConvSeg;
+typedef struct PPConvParams {
+  PPConvSeg seg[PP_CONV_MAX_SEG];
+  int nseg;
+  int n, H, W, KH, KW;
+  const float* w_packed;
+  int Cout;
+  const float* bias;
+  const float* pre; int ld_pre;
+  const float* res; int ld_res;
+  float* out; int ld_out;
+  int act; float slope; int post_relu; int round_tf32;
+  int bn, tile_w;
+} PPConvParams;
+int pp_conv2d_umma(const PPConvParams* prm, cudaStream_t stream);
+/* the tiling pp_conv2d_umma will use for `prm` (no launch): pixel tile, output-channel tile, CTA count, dynamic smem */
+int pp_conv2d_umma_plan(const PPConvParams* prm, int* tile_h, int* tile_w, int* bn, int* ctas, int* smem_bytes);
+/* Sampling half of torchvision.ops.deform_conv2d for DeformableAlignment / SecondOrderDeformableAlignment (same call
+ * sites as pp_deform_align): x [n][H][W][ld_x] (Cin = 128 | 256), o = raw conv_offset output [n*H*W][ld_o >= 432],
+ * o_bias [432] | NULL, flow [n*H*W][2] | NULL -> cols [n*H*W][9*Cin] (k*Cin + c), modulated samples rounded to TF32. */
+int pp_deform_gather(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
+                     float* cols, int n, int H, int W, int Cin, cudaStream_t stream);
 
 /* ---- generator glue ------------------------------------------------------------------------- */
 /* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar

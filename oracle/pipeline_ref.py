@@ -37,7 +37,13 @@ def to_float_frames(frames_u8):
     return (x * 2 - 1).unsqueeze(0)
 
 
-def stage_flow(sds, frames, raft_iter=20):
+def _ec(on, t):
+    """the reference's torch.cuda.empty_cache() calls (inference_propainter.py:323,360,395,452); no-op on CPU tensors"""
+    if on and t.is_cuda:
+        torch.cuda.empty_cache()
+
+
+def stage_flow(sds, frames, raft_iter=20, empty_cache=False):
     """:302-330."""
     T, W = frames.shape[1], frames.shape[-1]
     clip = raft_clip_len(W)
@@ -49,10 +55,11 @@ def stage_flow(sds, frames, raft_iter=20):
         a, b = raft_ref.raft_bi(sds["raft"], frames[:, max(f - 1, 0):e] if f else frames[:, f:e], raft_iter)
         ff.append(a)
         bb.append(b)
+        _ec(empty_cache, frames)
     return torch.cat(ff, 1), torch.cat(bb, 1)
 
 
-def stage_complete(sds, flows_bi, flow_masks, subvideo_length=80):
+def stage_complete(sds, flows_bi, flow_masks, subvideo_length=80, empty_cache=False):
     """:341-368."""
     L = flows_bi[0].shape[1]
     sd = sds["rfc"]
@@ -68,10 +75,11 @@ def stage_complete(sds, flows_bi, flow_masks, subvideo_length=80):
         pred = flowcomp_ref.combine_flow(sub, pred, flow_masks[:, s:e + 1])
         pf.append(pred[0][:, ps:e - s - pe])
         pb.append(pred[1][:, ps:e - s - pe])
+        _ec(empty_cache, flow_masks)
     return torch.cat(pf, 1), torch.cat(pb, 1)
 
 
-def stage_img_prop(frames, masks_dilated, pred_flows, subvideo_length=80):
+def stage_img_prop(frames, masks_dilated, pred_flows, subvideo_length=80, empty_cache=False):
     """:371-404."""
     T = frames.shape[1]
     masked = frames * (1 - masks_dilated)
@@ -88,6 +96,7 @@ def stage_img_prop(frames, masks_dilated, pred_flows, subvideo_length=80):
         upd = frames[:, s:e] * (1 - masks_dilated[:, s:e]) + prop * masks_dilated[:, s:e]
         uf.append(upd[:, ps:e - s - pe])
         umk.append(um[:, ps:e - s - pe])
+        _ec(empty_cache, frames)
     return torch.cat(uf, 1), torch.cat(umk, 1)
 
 
@@ -103,7 +112,7 @@ def window_plan(T, neighbor_length=10, ref_stride=10, subvideo_length=80):
 
 
 def stage_generate(sds, upd_frames, masks_dilated, upd_masks, pred_flows, ori_u8, neighbor_length=10,
-                   ref_stride=10, subvideo_length=80):
+                   ref_stride=10, subvideo_length=80, empty_cache=False):
     """:406-452 incl. uint8 truncation, masked composite and the order-dependent 1/2-1/2 blend."""
     T = upd_frames.shape[1]
     comp = [None] * T
@@ -121,19 +130,23 @@ def stage_generate(sds, upd_frames, masks_dilated, upd_masks, pred_flows, ori_u8
             else:
                 comp[idx] = comp[idx].astype(np.float32) * 0.5 + img.astype(np.float32) * 0.5
             comp[idx] = comp[idx].astype(np.uint8)
+        _ec(empty_cache, upd_frames)
     return np.stack(comp, 0)
 
 
 def run_pipeline(sds, frames_u8, flow_masks, masks_dilated, raft_iter=20, neighbor_length=10, ref_stride=10,
-                 subvideo_length=80, return_stages=False):
+                 subvideo_length=80, return_stages=False, empty_cache=False):
     """Whole path.  frames_u8 [T,H,W,3] uint8 (numpy); masks [1,T,1,H,W] float {0,1}."""
     frames = to_float_frames(frames_u8).to(masks_dilated.device)
     with torch.no_grad():
-        gt = stage_flow(sds, frames, raft_iter)
-        pred = stage_complete(sds, gt, flow_masks, subvideo_length)
-        upd_f, upd_m = stage_img_prop(frames, masks_dilated, pred, subvideo_length)
+        gt = stage_flow(sds, frames, raft_iter, empty_cache)
+        _ec(empty_cache, frames)                                           # :330
+        pred = stage_complete(sds, gt, flow_masks, subvideo_length, empty_cache)
+        _ec(empty_cache, frames)                                           # :368
+        upd_f, upd_m = stage_img_prop(frames, masks_dilated, pred, subvideo_length, empty_cache)
+        _ec(empty_cache, frames)                                           # :404
         comp = stage_generate(sds, upd_f, masks_dilated, upd_m, pred, np.asarray(frames_u8), neighbor_length,
-                              ref_stride, subvideo_length)
+                              ref_stride, subvideo_length, empty_cache)
     if return_stages:
         return comp, {"gt_flows": gt, "pred_flows": pred, "updated_frames": upd_f, "updated_masks": upd_m}
     return comp

@@ -1,0 +1,114 @@
+// Issue-rate probe for tcgen05.mma (sm_100a): how many cycles does one M=128 MMA cost as a function of N, of where A
+// comes from (shared memory descriptor vs TMEM) and of the shared-memory layout (K-major SWIZZLE_128B / SWIZZLE_32B /
+// no swizzle), for kind::tf32 (K = 8 per instruction) and kind::f16 (bf16, K = 16)?  One CTA, one elected lane issues
+// `iters` back-to-back MMAs into one accumulator (or alternating between two), commits, and the warp waits on the mbarrier;
+// cycles = clock64 around issue + completion.  Operands are zeros (only the rate matters here; layouts are validated by
+// umma_probe.cu and the parity tests).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate_probe umma_rate_probe.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t sm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect() {
+  uint32_t pred = 0;
+  asm volatile("{ .reg .b32 r; .reg .pred p; elect.sync r|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+
+// mode 0: SS SW128 tf32   1: TS (A in TMEM) SW128 B tf32   2: SS SW32 tf32   3: SS no-swizzle tf32   4: SS SW128 bf16   5: TS bf16
+__global__ void __launch_bounds__(128) rate(int mode, int N, int iters, int two_acc, int advance, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  if (warp == 0) {
+    const bool bf16 = mode >= 4, ts = (mode == 1 || mode == 5);
+    const uint32_t fmt = bf16 ? 1u : 2u;                           // a/b format: 1 = bf16 (kind::f16), 2 = tf32
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t layout = 2, sbo = 1024, lbo = 16, kstep = 32;         // SW128: 8-row groups 1 KB apart, k-step = 32 B inside the row
+    if (mode == 2) { layout = 6; sbo = 256; kstep = 4096; }        // SW32: rows of 32 B, one k-step = whole [128 x 32 B] slab
+    if (mode == 3) { layout = 0; sbo = 128; lbo = 2048; kstep = 4096; }   // interleaved 8x16B core matrices
+    const uint32_t a_addr = sm(smem), b_addr = sm(smem + 64 * 1024);
+    const uint64_t ad0 = make_desc(a_addr, lbo, sbo, layout), bd0 = make_desc(b_addr, lbo, sbo, layout);
+    const uint32_t tD0 = tb, tD1 = tb + 256, tA = tb + 384;
+    long long t0 = clock64();
+    if (elect()) {
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint64_t ad = ad0 + (advance ? (uint64_t)(((u * kstep) % 16384) >> 4) : 0);
+          const uint64_t bd = bd0 + (advance ? (uint64_t)(((u * kstep) % 16384) >> 4) : 0);
+          const uint32_t td = (two_acc && (u & 1)) ? tD1 : tD0;
+          if (!ts) {
+            if (!bf16) asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                                    ::"r"(td), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                              ::"r"(td), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+          } else {
+            if (!bf16) asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }"
+                                    ::"r"(td), "r"(tA + u * 8), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }"
+                              ::"r"(td), "r"(tA + u * 8), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm(&bar)) : "memory");
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 26) && !done; ++spin)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(sm(&bar)) : "memory");
+    long long t2 = clock64();
+    if (tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const char* names[6] = {"SS sw128 tf32", "TS tf32 (A in TMEM)", "SS sw32 tf32", "SS interleave tf32", "SS sw128 bf16", "TS bf16"};
+  const int iters = 512;
+  for (int mode = 0; mode < 6; ++mode)
+    for (int N = 32; N <= 256; N *= 2)
+      for (int two = 0; two < 2; ++two) {
+        if (two && N > 128) continue;
+        for (int adv = 0; adv < 2; ++adv) {
+          long long h[2] = {0, 0};
+          for (int rep = 0; rep < 2; ++rep) {
+            rate<<<1, 128, 200 * 1024>>>(mode, N, iters, two, adv, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("%s N=%d: %s\n", names[mode], N, cudaGetErrorString(e)); return 1; }
+            cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+          }
+          printf("%-22s N=%3d two_acc=%d advance=%d: issue %6.1f cyc/MMA, complete %6.1f cyc/MMA (ideal %5.1f)\n", names[mode], N, two, adv,
+                 (double)h[0] / iters, (double)h[1] / iters, mode >= 4 ? N / 2.0 : N / 2.0);
+        }
+      }
+  return 0;
+}

@@ -22,6 +22,23 @@ class PPAttnParams(ctypes.Structure):
                 ("kf_start", c_int), ("kf_step", c_int), ("nkf", c_int), ("scale_log2", c_float)]
 
 
+PP_CONV_MAX_SEG = 4
+
+
+class PPConvSeg(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld", c_int), ("C", c_int)]
+
+
+class PPConvParams(ctypes.Structure):
+    _fields_ = [("seg", PPConvSeg * PP_CONV_MAX_SEG), ("nseg", c_int),
+                ("n", c_int), ("H", c_int), ("W", c_int), ("KH", c_int), ("KW", c_int),
+                ("w_packed", c_void_p), ("Cout", c_int), ("bias", c_void_p),
+                ("pre", c_void_p), ("ld_pre", c_int), ("res", c_void_p), ("ld_res", c_int),
+                ("out", c_void_p), ("ld_out", c_int),
+                ("act", c_int), ("slope", c_float), ("post_relu", c_int), ("round_tf32", c_int),
+                ("bn", c_int), ("tile_w", c_int)]
+
+
 class PPWindowIds(ctypes.Structure):
     _fields_ = [("n", c_int), ("frame", c_int * PP_MAX_WINDOW), ("first", c_int * PP_MAX_WINDOW)]
 
@@ -46,6 +63,10 @@ SIGNATURES = {
     "pp_deform_align_batched_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pp_deform_align_batched": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pp_conv2d_umma": (c_int, [ctypes.POINTER(PPConvParams), c_void_p]),
+    "pp_conv2d_umma_plan": (c_int, [ctypes.POINTER(PPConvParams)] + [ctypes.POINTER(c_int)] * 5),
+    "pp_deform_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
     "pp_gen_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p]),
     "pp_window_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -86,7 +107,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if a symbol is missing
             fn.restype, fn.argtypes = res, args
-        if handle.pp_abi_version() != 1:
+        if handle.pp_abi_version() != 2:
             raise RuntimeError("libpropainter_b200.so ABI version mismatch")
         _lib = handle
     return _lib

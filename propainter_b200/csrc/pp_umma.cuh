@@ -33,6 +33,13 @@ __device__ __forceinline__ void ua_bar_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   if (!done) __trap();
 }
+// one lane of the (converged) warp: lets ptxas keep tcgen05 / TMA operands in uniform registers and predicate the single
+// instruction, instead of looping over the active lanes of a divergent region
+__device__ __forceinline__ bool ua_elect() {
+  uint32_t pred = 0;
+  asm volatile("{ .reg .b32 r; .reg .pred p; elect.sync r|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void ua_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

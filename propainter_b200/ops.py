@@ -6,7 +6,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import PPAttnParams, PPWindowIds, check
+from ._lib import PPAttnParams, PPConvParams, PPWindowIds, check
 
 LOG2E = 1.4426950408889634
 
@@ -154,6 +154,97 @@ def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
                             H, W, Cin, out.shape[-1], _p(ws), ws_bytes, _stream()), "pp_deform_align")
     _count(3)                                                    # tap pre-pass, GEMM, (split-K reduce)
     return out
+
+
+def tf32_round(w):
+    """fp32 -> nearest TF32 value (ties away from zero, = cvt.rna.tf32.f32), still stored as fp32.  tcgen05 kind::tf32
+    ignores the low 13 mantissa bits; rounding once at pack time keeps the products unbiased."""
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_conv_weight(weight, seg_channels=None):
+    """[Cout,Cin,KH,KW] -> [Cout,K] for pp_conv2d_umma: the input channels are split into the segments `seg_channels`
+    (default: one segment), every segment is zero-padded to 32-channel blocks and K runs ((blk*KH + dy)*KW + dx)*32 + c."""
+    Cout, Cin, KH, KW = weight.shape
+    seg_channels = [Cin] if seg_channels is None else list(seg_channels)
+    if sum(seg_channels) != Cin:
+        raise RuntimeError("pack_conv_weight: segments do not add up to Cin")
+    blocks, c0 = [], 0
+    for C in seg_channels:
+        for b in range(0, C, 32):
+            cw = min(32, C - b)
+            blk = weight.new_zeros(Cout, KH, KW, 32)
+            blk[..., :cw] = weight[:, c0 + b:c0 + b + cw].permute(0, 2, 3, 1)
+            blocks.append(blk.reshape(Cout, KH * KW * 32))
+        c0 += C
+    return tf32_round(torch.cat(blocks, 1).contiguous())
+
+
+def _pm4(t):
+    """[n,H,W,C] pixel-major view (unit channel stride, dense over n*H*W pixels) -> (ptr, ld)."""
+    if t.dim() != 4:
+        raise RuntimeError("expected [n,H,W,C]")
+    return _pm(t)
+
+
+def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pre=None, res=None, post_relu=False, out=None,
+              round_tf32=False, bn=0, tile_w=0):
+    """tcgen05 implicit-GEMM conv (stride 1, same padding) with fused epilogue.  segs: list of [n,H,W,C_i] pixel-major
+    views = the channel-concatenated input; w_packed from pack_conv_weight(weight, [C_i...]); pre / res / out
+    [n,H,W,Cout] views (channel slices of wider buffers allowed).  Returns out."""
+    n, H, W, _ = segs[0].shape
+    if out is None:
+        out = torch.empty(n, H, W, Cout, device=segs[0].device, dtype=torch.float32)
+    prm = PPConvParams()
+    prm.nseg = len(segs)
+    kblocks = 0
+    for i, sgm in enumerate(segs):
+        if tuple(sgm.shape[:3]) != (n, H, W):
+            raise RuntimeError("conv_umma: segment shape mismatch")
+        ptr, ld = _pm4(sgm)
+        prm.seg[i].x, prm.seg[i].ld, prm.seg[i].C = ptr.value, ld, sgm.shape[-1]
+        kblocks += (sgm.shape[-1] + 31) // 32
+    if tuple(w_packed.shape) != (Cout, kblocks * KH * KW * 32):
+        raise RuntimeError(f"conv_umma: packed weight {tuple(w_packed.shape)} does not match {(Cout, kblocks * KH * KW * 32)}")
+    prm.n, prm.H, prm.W, prm.KH, prm.KW = n, H, W, KH, KW
+    prm.w_packed, prm.Cout = _p(_dense(w_packed)).value, Cout
+    prm.bias = _p(bias).value if bias is not None else None
+    for name, t in (("pre", pre), ("res", res), ("out", out)):
+        if t is None:
+            setattr(prm, name, None)
+            setattr(prm, "ld_" + name, 0)
+            continue
+        if tuple(t.shape) != (n, H, W, Cout):
+            raise RuntimeError(f"conv_umma: {name} shape {tuple(t.shape)} != {(n, H, W, Cout)}")
+        ptr, ld = _pm4(t)
+        setattr(prm, name, ptr.value)
+        setattr(prm, "ld_" + name, ld)
+    prm.act, prm.slope, prm.post_relu, prm.round_tf32 = ACT[act], float(slope), int(bool(post_relu)), int(bool(round_tf32))
+    prm.bn, prm.tile_w = int(bn), int(tile_w)
+    check(_lib.lib().pp_conv2d_umma(ctypes.byref(prm), _stream()), "pp_conv2d_umma")
+    _count(1)
+    return out
+
+
+def deform_gather(x, o, flow, max_res, cols=None, o_bias=None):
+    """x [n,H,W,Cin] view, o [n,H,W,>=432] raw conv_offset output, flow [n,H,W,2] | None -> cols [n,H,W,9*Cin]
+    (modulated bilinear samples, k*Cin + c, TF32-rounded): the A operand of the deformable conv's GEMM."""
+    n, H, W, Cin = x.shape
+    xp, ldx = _pm4(x)
+    op, ldo = _pm4(o)
+    if cols is None:
+        cols = torch.empty(n, H, W, 9 * Cin, device=x.device, dtype=torch.float32)
+    check(_lib.lib().pp_deform_gather(xp, ldx, op, ldo, _p(o_bias), _p(_dense(flow)) if flow is not None else None, float(max_res),
+                                      _p(_dense(cols)), n, H, W, Cin, _stream()), "pp_deform_gather")
+    _count(1)
+    return cols
+
+
+def pack_deform_weight_umma(weight):
+    """deform-conv weight [Cout,Cin,3,3] -> [Cout, 9*Cin] with k = tap*Cin + c (the column order of deform_gather), TF32."""
+    co, ci = weight.shape[:2]
+    return tf32_round(weight.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous())
 
 
 def pack_deform_weight(weight):

@@ -133,10 +133,18 @@ def reference_pipeline(nets, u8, flow_masks, masks_dilated, raft_iter=20, neighb
     return np.stack(comp, 0), dict(gt_f=gt[0], gt_b=gt[1], pred_f=pred[0], pred_b=pred[1], upd_f=upd_f, upd_m=upd_m, win0=first_window)
 
 
-def summarize(name, comp, st, out_dir):
-    sub = lambda z: z[..., ::4, ::4].contiguous().numpy()
+def summarize(name, comp, st, out_dir, stride=4, md=None):
+    """stride: spatial subsampling of the stage tensors.  With `md` (the dilated masks) only the pixels of the composited
+    video inside the holes are stored (`comp_holes`, in np.nonzero order): outside them the video equals the input clip,
+    which the test regenerates from the seed -- this keeps the 80-frame fixtures at a few MB."""
+    sub = lambda z: z[..., ::stride, ::stride].contiguous().numpy()
+    if md is not None:
+        sel = md[0, :, 0].numpy() > 0
+        extra = dict(comp_holes=comp[sel], stride=np.array(stride))
+    else:
+        extra = dict(comp=comp)
     np.savez_compressed(
-        os.path.join(out_dir, name + ".npz"), comp=comp,
+        os.path.join(out_dir, name + ".npz"), **extra,
         gt_f=sub(st["gt_f"]), gt_b=sub(st["gt_b"]), pred_f=sub(st["pred_f"]), pred_b=sub(st["pred_b"]),
         upd_f=sub(st["upd_f"]), upd_m=np.packbits(st["upd_m"].numpy().astype(np.uint8)), win0=sub(st["win0"]),
         sums=np.array([st[k].double().abs().sum().item() for k in ("gt_f", "gt_b", "pred_f", "pred_b", "upd_f", "win0")]))
@@ -147,13 +155,25 @@ CASES = {
     "c1_8x128x128_square_it6": dict(T=8, H=128, W=128, mask="square", raft_iter=6, sub=80),
     # T > subvideo_length: halo chunking of stages 2/3 and bounded ref selection
     "chunk_23x128x128_ellipse_it2_sub10": dict(T=23, H=128, W=128, mask="ellipse", raft_iter=2, sub=10),
+    # BASELINE.json configs[1] = the benchmarked workload, full size (~10 min of CPU each; `--cases` selects)
+    "c2_80x240x432_ellipse_it20": dict(T=80, H=240, W=432, mask="ellipse", raft_iter=20, sub=80, stride=8, holes=True),
+    # configs[2] clip: 25 % border mask (video completion); the reference's CPU path is fp32 (inference_propainter.py:221-222)
+    "c3_80x240x432_border_it20": dict(T=80, H=240, W=432, mask="border", raft_iter=20, sub=80, stride=8, holes=True),
 }
+DEFAULT_CASES = ["c1_8x128x128_square_it6", "chunk_23x128x128_ellipse_it2_sub10"]
 
 if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", nargs="*", default=DEFAULT_CASES, choices=list(CASES))
+    ap.add_argument("--threads", type=int, default=0)
+    a = ap.parse_args()
+    if a.threads:
+        torch.set_num_threads(a.threads)
     nets = build_reference()
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    for name, c in CASES.items():
+    for name in a.cases:
+        c = CASES[name]
         u8, fm, md = synth.make_clip(c["T"], c["H"], c["W"], mask=c["mask"], seed=0)
         comp, st = reference_pipeline(nets, u8, fm, md, raft_iter=c["raft_iter"], subvideo_length=c["sub"])
-        summarize(name, comp, st, out_dir)
+        summarize(name, comp, st, out_dir, stride=c.get("stride", 4), md=md if c.get("holes") else None)
         print(name, "done", comp.shape, os.path.getsize(os.path.join(out_dir, name + ".npz")) // 1024, "KiB")
