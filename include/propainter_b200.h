@@ -67,14 +67,6 @@ size_t pp_deform_align_workspace_bytes(int H, int W);   /* decoded tap records +
 int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
                     const float* w_packed, const float* bias, float* out, int ld_out, int H, int W, int Cin, int Cout,
                     void* workspace, size_t ws_bytes, cudaStream_t stream);
-/* The same op on a batch of n maps: x [n][H][W][ld_x], o [n][H][W][ld_o], flow [n][H][W][2] | NULL, out [n][H][W][ld_out]
- * (the forward- and backward-flow nets of forward_bidirect_flow, model/recurrent_flow_completion.py:312-337, advance in
- * lock step: one launch set serves both). */
-size_t pp_deform_align_batched_workspace_bytes(int n, int H, int W);
-int pp_deform_align_batched(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
-                            float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int n, int H, int W,
-                            int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream);   /* o_bias: bias of conv_offset.6 if not yet added, else NULL */
-
 /* ---- tcgen05 convolution (conv_umma.cu) -------------------------------------------------------- */
 /* Stride-1 "same" KHxKW convolution + the epilogue that follows it in the reference, as one kernel:
  *   out = post_relu?( act( conv(cat(seg...), W) + bias + pre ) + res )        [optionally rounded to TF32 on store]
@@ -108,9 +100,17 @@ int pp_conv2d_umma(const PPConvParams* prm, cudaStream_t stream);
 int pp_conv2d_umma_plan(const PPConvParams* prm, int* tile_h, int* tile_w, int* bn, int* ctas, int* smem_bytes);
 /* Sampling half of torchvision.ops.deform_conv2d for DeformableAlignment / SecondOrderDeformableAlignment (same call
  * sites as pp_deform_align): x [n][H][W][ld_x] (Cin = 128 | 256), o = raw conv_offset output [n*H*W][ld_o >= 432],
- * o_bias [432] | NULL, flow [n*H*W][2] | NULL -> cols [n*H*W][9*Cin] (k*Cin + c), modulated samples rounded to TF32. */
-int pp_deform_gather(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
-                     float* cols, int n, int H, int W, int Cin, cudaStream_t stream);
+ * o_bias [432] | NULL, flow [n*H*W][2] | NULL -> cols [n*H*W][9*Cin] (k*Cin + c), modulated samples rounded to TF32.
+ * x2 != NULL: channels [Cin/2, Cin) come from a second map x2 [n][H][W][ld_x2] (x then holds channels [0, Cin/2)). */
+int pp_deform_gather(const float* x, int ld_x, const float* x2, int ld_x2, const float* o, int ld_o, const float* o_bias,
+                     const float* flow, float max_res, float* cols, int n, int H, int W, int Cin, cudaStream_t stream);
+/* flow_warp (model/modules/flow_loss_utils.py:6-45; bilinear, zeros padding, align_corners=True) of pixel-major feature
+ * maps and fbConsistencyCheck (model/propainter.py:22-31), batched: feat [n][h][w][ld_f] (C channels), fprop / fcheck
+ * [n][h][w][2] (x,y) -> warped [n][h][w][ld_w] (NULL to skip; feat may then be NULL), aux [n][h][w][ld_a >= 3] receives
+ * (fprop.x, fprop.y, valid) (NULL to skip; fcheck may then be NULL).  The per-step prologue of
+ * BidirectionalPropagation.forward model/propainter.py:146-148 when the concat buffers of pp_prop_cond are not wanted. */
+int pp_flow_warp_fbcheck(const float* feat, int ld_f, const float* fprop, const float* fcheck, float* warped, int ld_w,
+                         float* aux, int ld_a, int n, int h, int w, int C, int round_tf32, cudaStream_t stream);
 
 /* ---- generator glue ------------------------------------------------------------------------- */
 /* F.interpolate block of InpaintGenerator.forward model/propainter.py:338-342: flows planar

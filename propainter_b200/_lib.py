@@ -60,13 +60,12 @@ SIGNATURES = {
     "pp_deform_align_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pp_deform_align": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "pp_deform_align_batched_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "pp_deform_align_batched": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
-                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pp_conv2d_umma": (c_int, [ctypes.POINTER(PPConvParams), c_void_p]),
-    "pp_conv2d_umma_plan": (c_int, [ctypes.POINTER(PPConvParams)] + [ctypes.POINTER(c_int)] * 5),
-    "pp_deform_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
-                                 c_void_p]),
+    "pp_conv2d_umma_plan": (c_int, [ctypes.POINTER(PPConvParams)] + [c_void_p] * 5),
+    "pp_deform_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "pp_flow_warp_fbcheck": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_void_p]),
     "pp_gen_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p]),
     "pp_window_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -8,10 +8,9 @@ LINEAR_TF32     plain Linear layers of the transformer (q/k/v, proj, fc1, fc2 = 
 CUDNN_BENCHMARK let cuDNN autotune conv algorithms during graph warm-up.
 CUDA_GRAPHS     replay each stage as a captured CUDA graph per shape signature (propainter_b200/graphs.py).
 FUSED_EPILOGUE  conv bias + activation through pp_bias_act (one pass) instead of cuDNN's bias add_ + ATen activation.
-RFC_BATCHED     run the forward-flow and backward-flow nets of forward_bidirect_flow as one batch of two (every kernel of
-                the scans serves both; pp_deform_align_batched) instead of two concurrent streams.  The scans' kernels
-                occupy a fraction of the GPU, so batching should cost one scan instead of ~1.5 (two streams slow each
-                other down).  Off until it has been validated and timed on hardware.
+UMMA_CONV       the convolutions of the two recurrent propagation scans (offset nets, backbones, deformable-conv GEMM) run on
+                the tcgen05 implicit-GEMM kernel pp_conv2d_umma (TF32 products, fused bias / activation / residual / concat
+                epilogue) instead of cuDNN + pp_bias_act + the mma.sync deform kernel.
 AUTOTUNE        time numerically equivalent plans of a step once per shape during warm-up and keep the faster
                 (propainter_b200/autotune.py): grouped conv vs per-group dense convs, conv + pp_bias_act vs cuDNN's fused
                 conv-bias-ReLU.
@@ -25,7 +24,7 @@ CUDNN_BENCHMARK = True
 CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
-RFC_BATCHED = False
+UMMA_CONV = True
 
 
 @contextlib.contextmanager

@@ -23,10 +23,11 @@
 // UA_V_MN = 1: V tiles stay row-major (MN-major B operand in the SWIZZLE_128B_BASE32B layout, the only MN-major layout
 // tcgen05 accepts for 32-bit operands -- profiles/probes/umma_probe.cu variants 5/6), copied by cp.async like K: no
 // staging buffer, no transposing pass.  V then reaches the tensor core un-rounded (hardware truncation to TF32).
-// Measured on B200 (profiles/r1_attn_vmn_probe.log): 127 / 258 us vs 142 / 322 us (5/16, 16/16 windows masked), within
-// 1.8e-4 / 2.0e-3 of the mma.sync kernel.  Default stays 0 until the full parity suite has been run with it.
+// Measured on B200 with three stages (gpurun_out exp_vmn3, round 2): 110 / 215 us vs 135 / 312 us for the transposing
+// two-stage build (5/16, 16/16 windows masked), within 2.6e-4 / 2.3e-3 of the mma.sync kernel (the transposing build:
+// 2.1e-4 / 1.9e-3) -- the default since round 2; UA_V_MN=0 keeps the transposing producer for comparison.
 #ifndef UA_V_MN
-#define UA_V_MN 0
+#define UA_V_MN 1
 #endif
 #define UA_BM 128
 #define UA_BN 64
@@ -36,7 +37,7 @@
 #define UA_STAGE_BYTES (UA_K_BYTES + UA_V_BYTES)
 #define UA_LDSTG 132                               // V staging rows: 128 floats + 4 pad (conflict-free LDS.128 by key)
 #ifndef UA_STAGES
-#define UA_STAGES 2                                // K/V stages (one per producer group); 3 fits only with UA_V_MN=1 (untested)
+#define UA_STAGES (UA_V_MN ? 3 : 2)                // K/V stages; 3 fit only without the V staging buffers (UA_V_MN=1)
 #endif
 #if UA_V_MN
 #define UA_STG_BYTES 0                             // no V staging buffers
@@ -168,34 +169,49 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
       ua_bar_arrive(bar(s));
     }
   } else if (warp == 12) {
-    // ================================================= MMA issuer (one elected thread)
-    if (lane == 0) {
+    // ================================================= MMA issuer: the warp stays converged, one elected lane issues.
+    // (Inside a divergent `if (lane == 0)` region ptxas wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop and
+    // rebuilds its descriptors through R2UR moves: ~100 issue cycles per MMA, measured with the conv kernel's cycle
+    // counters -- more than the 32-64 cycles the MMA itself takes.  Descriptors are built once per tile and advanced by
+    // adding to their 16-byte address field.)
+    {
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24) |
                                (UA_V_MN ? (1u << 16) : 0u);               // bit 16: B operand MN-major
       auto issue_s = [&](int j) {                                        // caller has observed kv_full for tile j
         const int sb = j & 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t kaddr = ua_smem(base + (j % UA_STAGES) * UA_STAGE_BYTES);
+        const uint64_t kd = ua_desc(ua_smem(base + (j % UA_STAGES) * UA_STAGE_BYTES));
+        if (ua_elect()) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)                                   // 128 head dims = 4 k-blocks x 4 k-steps of 8; A = Q from TMEM
-          ua_mma_ts(tS0 + sb * UA_BN, tQ + ks * 8, ua_desc(kaddr + (ks >> 2) * (UA_BN * 128) + (ks & 3) * 32), idesc_s, ks > 0);
-        ua_commit(bar(6 + sb));                                          // S_j ready for the softmax warps
+          for (int ks = 0; ks < 16; ++ks)                                 // 128 head dims = 4 k-blocks x 4 k-steps of 8; A = Q from TMEM
+            ua_mma_ts(tS0 + sb * UA_BN, tQ + ks * 8, kd + (uint64_t)(((ks >> 2) * (UA_BN * 128) + (ks & 3) * 32) >> 4), idesc_s, ks > 0);
+          ua_commit(bar(6 + sb));                                        // S_j ready for the softmax warps
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int j) {
         const int sb = j & 1, st = j % UA_STAGES;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t vaddr = ua_smem(base + st * UA_STAGE_BYTES + UA_K_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < UA_BN / 8; ++ks)                            // 64 keys = 2 k-blocks x 4 k-steps
 #if UA_V_MN
-          ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, ua_desc_mn(vaddr + ks * 1024), idesc_o, (j > 0 || ks > 0));   // 8 key rows x 128 B
+        const uint64_t vd = ua_desc_mn(vaddr);
 #else
-          ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, ua_desc(vaddr + (ks >> 2) * (128 * 128) + (ks & 3) * 32), idesc_o,
-                    (j > 0 || ks > 0));
+        const uint64_t vd = ua_desc(vaddr);
 #endif
-        ua_commit(bar(3 + st));                                          // stage may be refilled
-        ua_commit(bar(10));                                              // O holds tiles 0..j
+        if (ua_elect()) {
+#pragma unroll
+          for (int ks = 0; ks < UA_BN / 8; ++ks)                          // 64 keys = 2 k-blocks x 4 k-steps
+#if UA_V_MN
+            ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, vd + (uint64_t)((ks * 1024) >> 4), idesc_o, (j > 0 || ks > 0));   // 8 key rows x 128 B
+#else
+            ua_mma_ts(tO, tP0 + sb * UA_BN + ks * 8, vd + (uint64_t)(((ks >> 2) * (128 * 128) + (ks & 3) * 32) >> 4), idesc_o,
+                      (j > 0 || ks > 0));
+#endif
+          ua_commit(bar(3 + st));                                        // stage may be refilled
+          ua_commit(bar(10));                                            // O holds tiles 0..j
+        }
+        __syncwarp();
       };
       ua_bar_wait(bar(11), 0);                                           // Q is in TMEM
       ua_bar_wait(bar(0), 0);
@@ -205,8 +221,8 @@ __global__ void __launch_bounds__(UA_THREADS, 1) k_sparse_attn_umma(PPAttnParams
         // or P_j.V_j (needs the softmax warps' P_j, and O rescaled if that was required)
         bool s_done = j + 1 >= ntiles, pv_done = false;
         for (long spin = 0; !(s_done && pv_done); ++spin) {
-          if (!s_done && ua_bar_test(bar((j + 1) % UA_STAGES), (((j + 1) / UA_STAGES) & 1))) { issue_s(j + 1); s_done = true; }
-          if (!pv_done && ua_bar_test(bar(8 + (j & 1)), (j >> 1) & 1)) { issue_pv(j); pv_done = true; }
+          if (!s_done && __any_sync(0xffffffffu, ua_bar_test(bar((j + 1) % UA_STAGES), (((j + 1) / UA_STAGES) & 1)))) { issue_s(j + 1); s_done = true; }
+          if (!pv_done && __any_sync(0xffffffffu, ua_bar_test(bar(8 + (j & 1)), (j >> 1) & 1))) { issue_pv(j); pv_done = true; }
           if (spin > (1L << 26)) __trap();
         }
       }

@@ -381,7 +381,8 @@ extern "C" int pp_conv2d_umma(const PPConvParams* q, cudaStream_t stream) {
 // 1x1 kernel over `cols`).  One warp per (pixel, tap): lane <-> (group, half of the group's channels), so a warp reads
 // 16 positions x 4 corners x 32/64 B and writes one contiguous Cin*4-byte run.
 template <int CPL>   // channels per lane: 4 (Cin = 128) or 8 (Cin = 256)
-__global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__ x, int ld_x, const float* __restrict__ o, int ld_o,
+__global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__ x, int ld_x, const float* __restrict__ x2, int ld_x2,
+    const float* __restrict__ o, int ld_o,
     const float* __restrict__ obias, const float* __restrict__ flow, float max_res, float* __restrict__ cols, long npix, int H, int W) {
   const long item = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (item >= npix * 9) return;
@@ -398,8 +399,13 @@ __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__
   const PPDW d = pp_deform_weights(t, H, W);
   constexpr int CIN = CPL * 32;
   const int c = g * (2 * CPL) + half * CPL;
+  // x2 != NULL: the input channels are split over two maps of CIN/2 channels each (offset groups 0-7 | 8-15): the two
+  // previous states of the second-order scan live in different slots of the history buffer (no torch.cat)
+  const bool second = x2 != nullptr && c >= CIN / 2;
+  if (second) { x = x2; ld_x = ld_x2; }
+  const int cs = second ? c - CIN / 2 : c;
   const float* xi = x + img * HW * ld_x;
-  const float* p00 = xi + ((long)d.y0 * W + d.x0) * ld_x + c;
+  const float* p00 = xi + ((long)d.y0 * W + d.x0) * ld_x + cs;
   const float wts[4] = {d.w00, d.w01, d.w10, d.w11};
   const float* q[4] = {p00, p00 + ld_x, p00 + (long)W * ld_x, p00 + (long)W * ld_x + ld_x};
   float4 acc[CPL / 4];
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float w = wts[j];
-    const float* a = w != 0.f ? q[j] : xi + c;                    // never dereference an out-of-image corner
+    const float* a = w != 0.f ? q[j] : xi + cs;                   // never dereference an out-of-image corner
 #pragma unroll
     for (int i = 0; i < CPL / 4; ++i) {
       const float4 v = *reinterpret_cast<const float4*>(a + 4 * i);
@@ -422,14 +428,15 @@ __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__
                                                           __uint_as_float(pp_tf32(acc[i].z)), __uint_as_float(pp_tf32(acc[i].w)));
 }
 
-extern "C" int pp_deform_gather(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow, float max_res,
-                                float* cols, int n, int H, int W, int Cin, cudaStream_t stream) {
+extern "C" int pp_deform_gather(const float* x, int ld_x, const float* x2, int ld_x2, const float* o, int ld_o, const float* o_bias,
+                                const float* flow, float max_res, float* cols, int n, int H, int W, int Cin, cudaStream_t stream) {
   if ((Cin != 128 && Cin != 256) || n < 1 || H < 1 || W < 1) return PP_ERR_SHAPE;
   if (ld_x % 4 || ld_o < 432 || ((uintptr_t)x & 15) || ((uintptr_t)cols & 15)) return PP_ERR_ALIGN;
+  if (x2 && (ld_x2 % 4 || ((uintptr_t)x2 & 15))) return PP_ERR_ALIGN;
   const long npix = (long)n * H * W;
   const long blocks = (npix * 9 + 7) / 8;
   if (blocks > 0x7fffffffL) return PP_ERR_SHAPE;
-  if (Cin == 128) k_deform_gather<4><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
-  else k_deform_gather<8><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
+  if (Cin == 128) k_deform_gather<4><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
+  else k_deform_gather<8><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
   return cudaPeekAtLastError() == cudaSuccess ? PP_OK : PP_ERR_LAUNCH;
 }

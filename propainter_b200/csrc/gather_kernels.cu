@@ -1,6 +1,7 @@
 // HBM/L2-bound gather, stencil and elementwise kernels of the ProPainter hot path (sm_100a).
 // One thread (or one warp) per output element; the per-element rules live in pp_elem.cuh.
 #include "pp_elem.cuh"
+#include "pp_mma.cuh"
 #include "../../include/propainter_b200.h"
 
 #define PP_LAUNCH_CHECK() do { if (cudaPeekAtLastError() != cudaSuccess) return PP_ERR_LAUNCH; } while (0)
@@ -107,6 +108,55 @@ extern "C" int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int
   const long n = (long)h * w;
   k_prop_cond<<<pp_blocks(n, 8), 256, 0, stream>>>(h, w, C, cur, ld_cur, prop, ld_prop, fprop, fcheck, mcur, cond,
                                                     ld_cond, bb, ld_bb, first);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// flow_warp + fbConsistencyCheck as a standalone op (SURVEY.md section 8b "flow_warp_fbcheck"), batched over n maps.
+// One warp per pixel; every lane derives the sampling position itself from the pixel's flow (two broadcast loads) instead
+// of waiting for lane 0 + shuffles, then gathers the 4 bilinear corners as float4 channel vectors (coalesced 512 B per
+// corner for C = 128).  `aux` (optional) receives (fx, fy, valid): the step-independent condition channels of
+// DeformableAlignment's offset net, so their share of conv_offset.0 can be convolved once per scan.
+__global__ void __launch_bounds__(256) k_flow_warp(long npix, int h, int w, int C, const float* __restrict__ feat, int ld_f,
+    const float* __restrict__ fprop, const float* __restrict__ fcheck, float* __restrict__ warped, int ld_w,
+    float* __restrict__ aux, int ld_a, int round_tf32) {
+  const int lane = threadIdx.x & 31;
+  const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const long HW = (long)h * w, img = pix / HW, pim = pix - img * HW;
+  const int y = (int)(pim / w), x = (int)(pim - (long)y * w);
+  const float* fp = fprop + img * HW * 2;
+  const float fx = fp[2 * pim], fy = fp[2 * pim + 1];
+  const float ix = pp_warp_coord((float)x, fx, w), iy = pp_warp_coord((float)y, fy, h);
+  const PPTaps t = pp_taps(ix, iy, h, w);
+  if (warped) {
+    const float* f = feat + img * HW * ld_f;
+    float* o = warped + pix * ld_w;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = pp_tap_nhwc4(f, ld_f, w, t, c);
+      if (round_tf32) {
+        v.x = __uint_as_float(pp_tf32(v.x)); v.y = __uint_as_float(pp_tf32(v.y));
+        v.z = __uint_as_float(pp_tf32(v.z)); v.w = __uint_as_float(pp_tf32(v.w));
+      }
+      *reinterpret_cast<float4*>(o + c) = v;
+    }
+  }
+  if (aux && lane == 0) {
+    const PPCond c = pp_cond_pixel(y, x, h, w, fp, fcheck + img * HW * 2);
+    float* a = aux + pix * ld_a;
+    a[0] = c.fx; a[1] = c.fy; a[2] = c.valid;
+  }
+}
+
+// flow_warp (model/modules/flow_loss_utils.py:6-45, bilinear / zeros / align_corners=True) of pixel-major maps and
+// fbConsistencyCheck (model/propainter.py:22-31); see include/propainter_b200.h
+extern "C" int pp_flow_warp_fbcheck(const float* feat, int ld_f, const float* fprop, const float* fcheck, float* warped, int ld_w,
+                                    float* aux, int ld_a, int n, int h, int w, int C, int round_tf32, cudaStream_t stream) {
+  if (n < 1 || h < 1 || w < 1 || (!warped && !aux)) return PP_ERR_SHAPE;
+  if (warped && (!feat || C % 4 || ld_f % 4 || ld_w % 4 || ((uintptr_t)feat & 15) || ((uintptr_t)warped & 15))) return PP_ERR_ALIGN;
+  if (aux && (!fcheck || ld_a < 3)) return PP_ERR_SHAPE;
+  const long npix = (long)n * h * w;
+  k_flow_warp<<<pp_blocks(npix, 8), 256, 0, stream>>>(npix, h, w, C, feat, ld_f, fprop, fcheck, warped, ld_w, aux, ld_a, round_tf32);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

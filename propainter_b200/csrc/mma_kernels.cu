@@ -127,23 +127,6 @@ __global__ void __launch_bounds__(256) k_deform_taps(const float* __restrict__ o
   taps[i] = make_float4((float)(y - 1 + k / 3) + oy, (float)(x - 1 + k % 3) + ox, 1.0f / (1.0f + expf(-ml)), 0.f);
 }
 
-// same for a batch of `nimg` maps stacked along the pixel index ([n][H][W] pixel-major): sampling coordinates are per image
-__global__ void __launch_bounds__(256) k_deform_taps_batched(const float* __restrict__ o, int ld_o, const float* __restrict__ obias,
-    const float* __restrict__ flow, float max_res, float4* __restrict__ taps, int nimg, int H, int W) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // (pix*9 + k)*16 + g
-  const long HW = (long)H * W;
-  if (i >= nimg * HW * 144) return;
-  const int g = (int)(i & 15); const long r = i >> 4; const int k = (int)(r % 9); const long pix = r / 9;
-  const long pim = pix % HW;
-  const int y = (int)(pim / W), x = (int)(pim - (long)y * W);
-  const float* op = o + pix * ld_o;
-  float oy = op[g * 18 + 2 * k], ox = op[g * 18 + 2 * k + 1], ml = op[288 + g * 9 + k];
-  if (obias) { oy += obias[g * 18 + 2 * k]; ox += obias[g * 18 + 2 * k + 1]; ml += obias[288 + g * 9 + k]; }
-  oy = max_res * tanhf(oy); ox = max_res * tanhf(ox);
-  if (flow) { oy += flow[2 * pix + 1]; ox += flow[2 * pix]; }
-  taps[i] = make_float4((float)(y - 1 + k / 3) + oy, (float)(x - 1 + k % 3) + ox, 1.0f / (1.0f + expf(-ml)), 0.f);
-}
-
 struct DARaw { float4 u[4], v[4]; float w[4]; };
 // issue the 8 corner loads of (tap position tp, 8 channels from c); corners with zero weight read a safe address
 __device__ __forceinline__ void da_issue(const float* __restrict__ x, int ld_x, const float4 tp, int H, int W, int c, bool valid,
@@ -179,17 +162,6 @@ __device__ __forceinline__ void da_combine(const DARaw& r, float4& s0, float4& s
 #undef DA_EXTRA_PARAMS
 #undef DA_NPIX
 #undef DA_REBASE
-// n maps stacked along the pixel index ([n][H][W] pixel-major): every pixel samples from its own map only
-#define DA_NAME k_deform_align_batched
-#define DA_EXTRA_PARAMS , int nimg
-#define DA_NPIX ((long)nimg * H * W)
-#define DA_REBASE x += (pixc / ((long)H * W)) * ((long)H * W) * ld_x;
-#include "deform_align_body.inc"
-#undef DA_NAME
-#undef DA_EXTRA_PARAMS
-#undef DA_NPIX
-#undef DA_REBASE
-
 __global__ void __launch_bounds__(256) k_deform_reduce(const float* __restrict__ part, const float* __restrict__ bias,
                                                        float* __restrict__ out, int ld_out, long npix, int splits) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // over npix*32 float4
@@ -237,29 +209,6 @@ extern "C" int pp_deform_align(const float* x, int ld_x, const float* o, int ld_
   k_deform_taps<<<(int)((npix * 144 + 255) / 256), 256, 0, stream>>>(o, ld_o, o_bias, flow, max_res, taps, H, W);
   dim3 grid((unsigned)((npix + 31) / 32), splits);
   k_deform_align<<<grid, 128, 0, stream>>>(x, ld_x, taps, w_packed, bias, out, ld_out, H, W, Cin, part);
-  if (splits > 1)
-    k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>(part, bias, out, ld_out, npix, splits);
-  PP_LAUNCH_CHECK();
-  return PP_OK;
-}
-
-// the same op on a batch of n maps ([n][H][W][ld] pixel-major; flow [n][H][W][2]): one launch set for all of them.  The
-// recurrent scans run on 1620- / 6480-pixel maps whose kernels fill a fraction of the GPU, so two independent scans
-// (the forward- and backward-flow nets of RecurrentFlowCompleteNet.forward_bidirect_flow) cost what one does.
-extern "C" size_t pp_deform_align_batched_workspace_bytes(int n, int H, int W) { return pp_deform_align_workspace_bytes(n * H, W); }
-extern "C" int pp_deform_align_batched(const float* x, int ld_x, const float* o, int ld_o, const float* o_bias, const float* flow,
-                                       float max_res, const float* w_packed, const float* bias, float* out, int ld_out, int n,
-                                       int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream) {
-  if (Cout != 128 || Cin % 32 || (Cin / 16) % 8 || n < 1) return PP_ERR_SHAPE;
-  if (ld_x % 4 || ld_out % 4 || ld_o < 432 || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)x & 15)) return PP_ERR_ALIGN;
-  const long npix = (long)n * H * W;
-  const int splits = da_splits(npix, 9 * (Cin / 32));
-  if (ws_bytes < pp_deform_align_batched_workspace_bytes(n, H, W) || ((uintptr_t)workspace & 15)) return PP_ERR_WORKSPACE;
-  float4* taps = (float4*)workspace;
-  float* part = (float*)(taps + npix * 144);
-  k_deform_taps_batched<<<(int)((npix * 144 + 255) / 256), 256, 0, stream>>>(o, ld_o, o_bias, flow, max_res, taps, n, H, W);
-  dim3 grid((unsigned)((npix + 31) / 32), splits);
-  k_deform_align_batched<<<grid, 128, 0, stream>>>(x, ld_x, taps, w_packed, bias, out, ld_out, H, W, Cin, part, n);
   if (splits > 1)
     k_deform_reduce<<<(int)((npix * 32 + 255) / 256), 256, 0, stream>>>(part, bias, out, ld_out, npix, splits);
   PP_LAUNCH_CHECK();
@@ -579,7 +528,7 @@ __global__ void __launch_bounds__(128, 2) k_attn_unmasked_frames(PPAttnParams p,
 int pp_launch_sparse_attn_umma(const PPAttnParams& p, int n_windows, cudaStream_t stream);   // attn_umma.cu
 
 static int pp_attn_check(const PPAttnParams& p) {
-  if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 4) return PP_ERR_SHAPE;
+  if (p.C != 512 || p.WN > 64 || p.WN < 1 || p.ld_qkv % 4 || p.ld_pool % 4 || p.ld_out % 4 || p.nkf < 0) return PP_ERR_SHAPE;
   if (((uintptr_t)p.qkv & 15) || ((uintptr_t)p.pool & 15) || ((uintptr_t)p.out & 15)) return PP_ERR_ALIGN;
   return PP_OK;
 }
@@ -613,8 +562,12 @@ extern "C" int pp_sparse_window_attn(const PPAttnParams* prm, int n_windows, cud
   const PPAttnParams& p = *prm;
   int rc = pp_attn_check(p);
   if (rc != PP_OK) return rc;
-  rc = pp_launch_sparse_attn_umma(p, n_windows, stream);
-  if (rc != PP_OK) return rc;
+  // nkf == 0 (t = 1 on an odd layer: T_ind is empty, sparse_transformer.py:339): masked windows attend to an empty key set,
+  // for which the reference's softmax-then-matmul yields zeros -- the caller pre-zeroes `out` and only the unmasked windows run
+  if (p.nkf > 0) {
+    rc = pp_launch_sparse_attn_umma(p, n_windows, stream);
+    if (rc != PP_OK) return rc;
+  }
   return pp_attn_unmasked(p, n_windows, stream);
 }
 
@@ -623,6 +576,7 @@ extern "C" int pp_sparse_window_attn_mma(const PPAttnParams* prm, int n_windows,
   const PPAttnParams& p = *prm;
   int rc = pp_attn_check(p);
   if (rc != PP_OK) return rc;
+  if (p.nkf <= 0) return pp_attn_unmasked(p, n_windows, stream);     // see pp_sparse_window_attn
   const int smem = 2 * AT_STAGE * (int)sizeof(float);
   if (cudaFuncSetAttribute(k_sparse_attn<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return PP_ERR_LAUNCH;

@@ -11,9 +11,29 @@ import torch
 from . import config, ops
 
 
+_POOLS = {}
+
+
+def _shared_pool(device_index):
+    """One private memory pool per device shared by every captured graph (torch.cuda.graph(pool=...)): graphs are replayed
+    one stage after another (or on side streams that each own a distinct graph instance per slot), so their intermediates
+    can share blocks instead of every capture keeping its own pool for the lifetime of the cache."""
+    if device_index not in _POOLS:
+        _POOLS[device_index] = torch.cuda.graph_pool_handle()
+    return _POOLS[device_index]
+
+
+def _switches():
+    """execution switches that are baked into a capture: part of the cache key, so flipping one re-captures"""
+    return (config.LINEAR_TF32, config.FUSED_EPILOGUE, config.AUTOTUNE, config.CUDNN_BENCHMARK, config.UMMA_CONV,
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+
 class GraphCache:
-    def __init__(self, enabled=True, warmup=2):
-        self.enabled, self.warmup, self.entries = enabled, warmup, {}
+    """max_entries bounds the number of live captures (least recently used is dropped; its memory returns to the pool)."""
+
+    def __init__(self, enabled=True, warmup=2, max_entries=64):
+        self.enabled, self.warmup, self.entries, self.max_entries = enabled, warmup, {}, max_entries
 
     def clear(self):
         self.entries = {}
@@ -23,9 +43,13 @@ class GraphCache:
         Returned tensors are fresh clones, so callers may keep them across replays."""
         if not (self.enabled and config.CUDA_GRAPHS) or not inputs[0].is_cuda:
             return fn(*inputs)
-        key = (key,) + tuple((tuple(x.shape), x.dtype, x.device.index) for x in inputs)
-        e = self.entries.get(key)
+        key = (key, _switches()) + tuple((tuple(x.shape), x.dtype, x.device.index) for x in inputs)
+        e = self.entries.pop(key, None)
+        if e is not None:
+            self.entries[key] = e                                   # re-insert: most recently used last
         if e is None:
+            while len(self.entries) >= self.max_entries:
+                self.entries.pop(next(iter(self.entries)))
             static_in = [x.detach().clone() for x in inputs]
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -37,7 +61,7 @@ class GraphCache:
             torch.cuda.synchronize()
             l0 = ops.LAUNCHES
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), config.cudnn_autotune():
+            with torch.cuda.graph(graph, pool=_shared_pool(inputs[0].device.index)), config.cudnn_autotune():
                 out = fn(*static_in)
             e = (graph, static_in, out, ops.LAUNCHES - l0)
             ops.LAUNCHES = l0                                   # capture records launches, it does not run them

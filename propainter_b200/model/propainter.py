@@ -8,7 +8,7 @@ discriminators (:378-532) are training-only and not part of the inference path.
 import torch
 import torch.nn.functional as F
 
-from .. import autotune, ops
+from .. import autotune, config, ops
 from .._params import ParamNet
 from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels, up2
 from ..schemas import generator_schema
@@ -155,6 +155,79 @@ class InpaintGenerator(ParamNet):
         z = conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2)
         return conv(z, self._wb(fp + "fuse.2"), 1, 1, res=as_nchw(x))
 
+    # ---- the same scan on the tcgen05 conv kernel (config.UMMA_CONV)
+    def _uw(self, key, sel, segs):
+        """packed weight of conv `key` restricted to the input channels `sel` (list of (lo, hi)) split into segments `segs`"""
+        def build():
+            w = self.P[key + ".weight"]
+            return ops.pack_conv_weight(torch.cat([w[:, lo:hi] for lo, hi in sel], 1), segs)
+        return self.packed(f"uw:{key}:{sel}:{segs}", build)
+
+    def _ub(self, key):
+        return self.P[key + ".bias"]
+
+    def _feat_propagation_umma(self, x, dsf, dsb, pmask):
+        """`_feat_propagation` with every conv of the scan on pp_conv2d_umma (tcgen05, TF32 products, fused bias /
+        activation / residual / placement epilogues, multi-segment inputs instead of concat buffers) and the deformable
+        conv as pp_deform_gather + a 1x1 pp_conv2d_umma.  Only the part of each conv that depends on the recurrent state
+        stays inside the sequential loop: conv(cat[a, b]) = conv_a(a) + conv_b(b), so the shares of conv_offset.0 and
+        backbone.0 that see the current frame, the flow / validity / mask channels (all known before the scan starts) are
+        convolved once per scan for all frames in one batched launch and enter the step as a pre-activation addend.
+        Per step: 1 warp + 4 offset convs + gather + GEMM + 2 backbone convs = 9 launches (before: ~17), K on the critical
+        path 7 x 1152 (before: 2376 + 3 x 1152 + 1152 + 2340 + 1152)."""
+        lt, h, w, C = x.shape
+        dev = x.device
+        fp = "feat_prop_module."
+        U = ops.conv_umma
+        aux = torch.zeros(lt, h, w, 8, device=dev)                  # [fx fy valid m0 m1 0 0 0]: step-independent condition channels
+        aux[..., 3:5] = pmask
+        mpad = torch.zeros(lt, h, w, 4, device=dev)                 # mask as a 16-byte aligned segment
+        mpad[..., :2] = pmask
+        warp = torch.empty(1, h, w, C, device=dev)
+        t1, t2, t3, y = (torch.empty(1, h, w, C, device=dev) for _ in range(4))
+        o = torch.empty(1, h, w, 432, device=dev)
+        cols = torch.empty(1, h, w, 9 * C, device=dev)
+        albuf = torch.empty(1, h, w, C, device=dev)
+        src, outs = x, {}
+        for name in ("backward_1", "forward_1"):
+            bwd = name == "backward_1"
+            order = list(range(lt))[::-1] if bwd else list(range(lt))
+            po, pb = f"{fp}deform_align.{name}.conv_offset.", f"{fp}backbone.{name}."
+            if lt > 1:                                              # (fx, fy, valid) of every frame that has a flow in this direction
+                if bwd:
+                    ops.flow_warp_fbcheck(None, dsf, dsb, aux=aux[:lt - 1, :, :, :3], want_warp=False)
+                else:
+                    ops.flow_warp_fbcheck(None, dsb, dsf, aux=aux[1:, :, :, :3], want_warp=False)
+            # conv_offset.0 input = [cur 0:128 | warped 128:256 | flow 256:258 | valid 258 | mask 259:261] (propainter.py:151);
+            # backbone.0 input = [cur 0:128 | aligned 128:256 | mask 256:258] (:171)
+            pre_off = U([src, aux[..., :5]], self._uw(po + "0", ((0, C), (2 * C, 2 * C + 5)), (C, 5)), 3, 3, C, bias=self._ub(po + "0"))
+            pre_bb = U([src, mpad[..., :2]], self._uw(pb + "0", ((0, C), (2 * C, 2 * C + 2)), (C, 2)), 3, 3, C, bias=self._ub(pb + "0"))
+            dst = torch.empty(lt, h, w, C, device=dev)
+            dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(self.P[f"{fp}deform_align.{name}.weight"]))
+            dbias = self.P[f"{fp}deform_align.{name}.bias"]
+            prev = None
+            for i, idx in enumerate(order):
+                if i == 0:
+                    al = src[idx:idx + 1]                            # feat_prop = feat_current (:141-143)
+                else:
+                    fprop = (dsf[idx] if bwd else dsb[idx - 1])[None]
+                    ops.flow_warp_fbcheck(prev, fprop, warped=warp, round_tf32=True)
+                    U([warp], self._uw(po + "0", ((C, 2 * C),), (C,)), 3, 3, C, pre=pre_off[idx:idx + 1], act="leaky", slope=0.1,
+                      out=t1, round_tf32=True)
+                    U([t1], self._uw(po + "2", ((0, C),), (C,)), 3, 3, C, bias=self._ub(po + "2"), act="leaky", slope=0.1, out=t2, round_tf32=True)
+                    U([t2], self._uw(po + "4", ((0, C),), (C,)), 3, 3, C, bias=self._ub(po + "4"), act="leaky", slope=0.1, out=t3, round_tf32=True)
+                    U([t3], self._uw(po + "6", ((0, C),), (C,)), 3, 3, 432, bias=self._ub(po + "6"), out=o)
+                    ops.deform_gather(prev, o, fprop, 3.0, cols)
+                    al = U([cols], dwp, 1, 1, C, bias=dbias, out=albuf)
+                U([al], self._uw(pb + "0", ((C, 2 * C),), (C,)), 3, 3, C, pre=pre_bb[idx:idx + 1], act="leaky", slope=0.2, out=y, round_tf32=True)
+                # feat(idx) = aligned + backbone(...) (:173-176)
+                prev = U([y], self._uw(pb + "2", ((0, C),), (C,)), 3, 3, C, bias=self._ub(pb + "2"), res=al, out=dst[idx:idx + 1])
+            outs[name] = dst
+            src = dst                                            # forward scan consumes the backward features (:138)
+        z = U([outs["backward_1"], outs["forward_1"], mpad[..., :2]], self._uw(fp + "fuse.0", ((0, 2 * C + 2),), (C, C, 2)), 3, 3, C,
+              bias=self._ub(fp + "fuse.0"), act="leaky", slope=0.2, round_tf32=True)
+        return as_nchw(U([z], self._uw(fp + "fuse.2", ((0, C),), (C,)), 3, 3, C, bias=self._ub(fp + "fuse.2"), res=x))
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def encode(self, masked_frames, masks_in, masks_updated, chunk=40):
@@ -210,7 +283,12 @@ class InpaintGenerator(ParamNet):
         H2, W2 = padded_grid(fh, fw, WIN)
         flags = ops.window_mask(pmask, fh, fw, H2 // WIN[0], W2 // WIN[1])
         enc_pm = as_pm(enc)
-        local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
+        if config.UMMA_CONV:
+            if interpolation != "bilinear":
+                raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
+            local = self._feat_propagation_umma(enc_pm[:lt], dsf, dsb, pmask)
+        else:
+            local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
         enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
         tok = self.tx.soft_split(enc2)
         tok = self.tx.run(tok, (h, w), flags, t_dilation)

@@ -63,18 +63,12 @@ class RecurrentFlowCompleteNet(ParamNet):
         return self.packed("dcn:" + name, build)
 
     # ------------------------------------------------------------------ blocks
-    def _p3d(self, p, x, stride, act="leaky", nb=1):
-        """P3DBlock :148-169 on a frame batch x [t,c,h,w] (channels_last); nb > 1: nb clips of t/nb frames each."""
+    def _p3d(self, p, x, stride, act="leaky"):
+        """P3DBlock :148-169 on a frame batch x [t,c,h,w] (channels_last)."""
         y = conv(x, self._w2d(p + ".conv1.0"), stride, 1, act="leaky", slope=0.2)
         t = y.shape[0]
-        if nb == 1:
-            yp = F.pad(y, (0, 0, 0, 0, 0, 0, 2, 2))                         # zero-pad time by 2 (padding=(2,0,0))
-            z = torch.cat([yp[0:t], yp[2:t + 2], yp[4:t + 4]], 1)            # dilation 2 taps
-        else:                                                               # the temporal taps must not cross clips
-            tc = t // nb
-            ypm = as_pm(y)
-            yp = F.pad(ypm.view(nb, tc, *ypm.shape[1:]), (0, 0, 0, 0, 0, 0, 2, 2))
-            z = as_nchw(torch.cat([yp[:, 0:tc], yp[:, 2:tc + 2], yp[:, 4:tc + 4]], -1).view(t, *ypm.shape[1:3], -1))
+        yp = F.pad(y, (0, 0, 0, 0, 0, 0, 2, 2))                             # zero-pad time by 2 (padding=(2,0,0))
+        z = torch.cat([yp[0:t], yp[2:t + 2], yp[4:t + 4]], 1)                # dilation 2 taps
         return conv(z, self._wt(p + ".conv2.0"), act=act, slope=0.2)
 
     def _up2_conv(self, key, x, act="none", res=None):
@@ -117,41 +111,65 @@ class RecurrentFlowCompleteNet(ParamNet):
             results[name] = seq.flip(0) if di == 0 else seq
         return conv(as_nchw(torch.cat([results["backward_"], results["forward_"]], -1)), self._w2d(fp + "fusion"), res=x)
 
-    def _propagate_batched(self, x, nb):
-        """`_propagate` for nb independent clips advancing in lock step: x [nb*t,128,h,w] (clip-major).  Same math per
-        clip; every conv / epilogue / deform launch of a step serves all clips (config.RFC_BATCHED)."""
-        T, c, h, w = x.shape
-        t = T // nb
+    def _uw(self, key, sel, segs):
+        """packed weight of conv `key` restricted to the input channels `sel` (list of (lo, hi)), split into segments `segs`"""
+        def build():
+            w = self.P[key + ".weight"]
+            if w.dim() == 5:
+                w = w[:, :, 0]
+            return ops.pack_conv_weight(torch.cat([w[:, lo:hi] for lo, hi in sel], 1), segs)
+        return self.packed(f"uw:{key}:{sel}:{segs}", build)
+
+    def _propagate_umma(self, x):
+        """`_propagate` on the tcgen05 conv kernel (config.UMMA_CONV): every conv of the scan is one pp_conv2d_umma launch
+        with its bias / LeakyReLU / residual / placement fused, the two previous states are read as two input segments straight
+        from the history buffer (no torch.cat), the deformable conv is pp_deform_gather (split input) + a 1x1 conv over the
+        sampled columns, and the shares of conv_offset.0 / backbone.0 that only see the current frame (and, in the forward
+        scan, the finished backward features) are convolved for all frames at once before the scan starts and enter the step
+        as a pre-activation addend (conv is linear in its input channels).  8 launches per step (before: ~17)."""
+        t, c, h, w = x.shape
         dev = x.device
-        xs = as_pm(x).view(nb, t, h, w, c)
+        xs = as_pm(x)                                                         # [t,h,w,128]
         fp = "feat_prop_module."
+        U = ops.conv_umma
+        P = self.P
+        t1, t2, t3, y = (torch.empty(1, h, w, c, device=dev) for _ in range(4))
+        o = torch.empty(1, h, w, 432, device=dev)
+        cols = torch.empty(1, h, w, 9 * 2 * c, device=dev)
+        albuf = torch.empty(1, h, w, c, device=dev)
+        zero = torch.zeros(1, h, w, c, device=dev)
         results = {}
         for di, name in enumerate(("backward_", "forward_")):
             order = list(range(t))[::-1] if di == 0 else list(range(t))
-            hist = torch.zeros(t + 2, nb, h, w, c, device=dev)
-            k = 2 + di
-            fall = torch.empty(t, nb, h, w, k * c, device=dev)
-            fall[..., :c] = xs.transpose(0, 1)
-            if di == 1:
-                fall[..., c:2 * c] = results["backward_"]
-            fall[order[0], ..., -c:] = 0
-            dw, db = self._dcn(name)
+            po, pb = f"{fp}deform_align.{name}.conv_offset.", f"{fp}backbone.{name}."
+            hist = torch.zeros(t + 2, h, w, c, device=dev)                   # slots 0,1 = zero states
+            # conv_offset.0 input = [prop 0:128 | cur 128:256 | n2 256:384] (:93-96); backbone.0 input = [cur | (backward feats) | aligned] (:101-106)
+            pre_off = U([xs], self._uw(po + "0", ((c, 2 * c),), (c,)), 3, 3, c, bias=P[po + "0.bias"])
+            k = 1 + di
+            hsegs = [xs] + ([results["backward_"]] if di == 1 else [])
+            pre_bb = U(hsegs, self._uw(pb + "0", ((0, k * c),), (c,) * k), 3, 3, c, bias=P[pb + "0.bias"])
+            dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(P[f"{fp}deform_align.{name}.weight"]))
+            dbias = P[f"{fp}deform_align.{name}.bias"]
             for i, idx in enumerate(order):
-                pslot = fall[idx, ..., -c:]                                   # [nb,h,w,128] view, pixel stride k*128
                 if i > 0:
-                    buf = torch.cat([hist[i + 1], hist[i], xs[:, idx]], -1)   # [nb,h,w,384]
-                    o = conv(as_nchw(buf), self._offset_w0(name), 1, 1, act="leaky", slope=0.1)
-                    o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.2"), 1, 1, act="leaky", slope=0.1)
-                    o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1, act="leaky", slope=0.1)
-                    w6, b6 = self._w2d(f"{fp}deform_align.{name}.conv_offset.6")
-                    o = as_pm(F.conv2d(o, w6, None, padding=1))
-                    ops.deform_align(buf[..., :256], o, None, 5.0, dw, db, pslot, o_bias=b6)
-                y = conv(as_nchw(fall[idx]), self._w2d(f"{fp}backbone.{name}.0"), 1, 1, act="leaky", slope=0.1)
-                conv(y, self._w2d(f"{fp}backbone.{name}.2"), 1, 1, res=as_nchw(pslot), out=as_nchw(hist[i + 2]))
-            seq = hist[2:]                                                   # [t,nb,h,w,c] in scan order
+                    s1, s2 = hist[i + 1:i + 2], hist[i:i + 1]                 # state(i-1), state(i-2)
+                    U([s1, s2], self._uw(po + "0", ((0, c), (2 * c, 3 * c)), (c, c)), 3, 3, c, pre=pre_off[idx:idx + 1], act="leaky", slope=0.1,
+                      out=t1, round_tf32=True)
+                    U([t1], self._uw(po + "2", ((0, c),), (c,)), 3, 3, c, bias=P[po + "2.bias"], act="leaky", slope=0.1, out=t2, round_tf32=True)
+                    U([t2], self._uw(po + "4", ((0, c),), (c,)), 3, 3, c, bias=P[po + "4.bias"], act="leaky", slope=0.1, out=t3, round_tf32=True)
+                    U([t3], self._uw(po + "6", ((0, c),), (c,)), 3, 3, 432, bias=P[po + "6.bias"], out=o)
+                    ops.deform_gather(s1, o, None, 5.0, cols, x2=s2)
+                    al = U([cols], dwp, 1, 1, c, bias=dbias, out=albuf)
+                else:
+                    al = zero                                                # step 0 propagates the zero state
+                U([al], self._uw(pb + "0", (((k) * c, (k + 1) * c),), (c,)), 3, 3, c, pre=pre_bb[idx:idx + 1], act="leaky", slope=0.1, out=y,
+                  round_tf32=True)
+                # state(i) = aligned + backbone(...) (:108-110)
+                U([y], self._uw(pb + "2", ((0, c),), (c,)), 3, 3, c, bias=P[pb + "2.bias"], res=al, out=hist[i + 2:i + 3])
+            seq = hist[2:]
             results[name] = seq.flip(0) if di == 0 else seq
-        both = torch.cat([results["backward_"], results["forward_"]], -1).transpose(0, 1).reshape(T, h, w, 2 * c)
-        return conv(as_nchw(both), self._w2d(fp + "fusion"), res=x)
+        return as_nchw(U([results["backward_"], results["forward_"]], self._uw(fp + "fusion", ((0, 2 * c),), (c, c)), 1, 1, c,
+                         bias=P[fp + "fusion.bias"], res=xs))
 
     # ------------------------------------------------------------------ API
     @torch.no_grad()
@@ -162,20 +180,19 @@ class RecurrentFlowCompleteNet(ParamNet):
                 for bi in range(b)]
         return torch.stack(outs, 0).view(b, t, 2, h, w).to(masked_flows.dtype), None
 
-    def _forward_one(self, flows, masks, nb=1):
-        """one clip: flows [t,2,h,w], masks [t,1,h,w] -> [t,2,h,w]; captured as a CUDA graph per shape.
-        nb > 1: nb clips stacked along the frame axis (clip-major), processed as one batch."""
+    def _forward_one(self, flows, masks):
+        """one clip: flows [t,2,h,w], masks [t,1,h,w] -> [t,2,h,w]; captured as a CUDA graph per shape."""
         x = torch.cat([flows, masks], 1)                                         # [t,3,h,w]
         x = F.pad(x, (2, 2, 2, 2), mode="replicate").contiguous(memory_format=torch.channels_last)
         x = conv(x, self._w2d("downsample.0"), 2, 0, act="leaky", slope=0.2)
-        e1 = self._p3d("encoder1.0", x, 1, nb=nb)
-        e1 = self._p3d("encoder1.2", e1, 2, nb=nb)
-        e2 = self._p3d("encoder2.0", e1, 1, nb=nb)
-        e2 = self._p3d("encoder2.2", e2, 2, nb=nb)
+        e1 = self._p3d("encoder1.0", x, 1)
+        e1 = self._p3d("encoder1.2", e1, 2)
+        e2 = self._p3d("encoder2.0", e1, 1)
+        e2 = self._p3d("encoder2.2", e2, 2)
         m = e2
         for i, d in ((0, 3), (2, 2), (4, 1)):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
-        fpr = self._propagate(m) if nb == 1 else self._propagate_batched(m, nb)
+        fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
         d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
         d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
         fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
@@ -190,7 +207,7 @@ class RecurrentFlowCompleteNet(ParamNet):
         b, t, _, h, w = xf.shape
         pf, pb = [], []
         for bi in range(b):
-            f, g = self.graphs(("rfc_bi", config.RFC_BATCHED), self._forward_pair, xf[bi].contiguous().float(), mf[bi].contiguous().float(),
+            f, g = self.graphs("rfc_bi", self._forward_pair, xf[bi].contiguous().float(), mf[bi].contiguous().float(),
                                xb[bi].contiguous().float(), mbf[bi].contiguous().float())
             pf.append(f)
             pb.append(g)
@@ -202,9 +219,6 @@ class RecurrentFlowCompleteNet(ParamNet):
         """The two directions are independent recurrent scans over 30x54 maps (312 strictly sequential, latency-bound
         deformable steps per 80-frame clip): run them on two streams so their kernels interleave on the GPU.  Inside a
         CUDA-graph capture this becomes two parallel branches of one graph."""
-        if config.RFC_BATCHED:                       # both directions as one batch of two (same weights, same schedule)
-            both = self._forward_one(torch.cat([xf, xb], 0), torch.cat([mf, mb], 0), nb=2)
-            return both[:xf.shape[0]], both[xf.shape[0]:]
         if not xf.is_cuda:
             return self._forward_one(xf, mf), self._forward_one(xb, mb)
         cur = torch.cuda.current_stream()
@@ -214,6 +228,8 @@ class RecurrentFlowCompleteNet(ParamNet):
             ob = self._forward_one(xb, mb)
         of = self._forward_one(xf, mf)
         cur.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            ob.record_stream(cur)            # allocated on `side`, consumed on `cur`: keep the block until cur is done with it
         return of, ob
 
     @torch.no_grad()

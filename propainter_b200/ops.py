@@ -129,20 +129,8 @@ def prop_cond(cur, prop, fprop, fcheck, mcur, cond, bb, first):
 
 def deform_align(x, o, flow, max_res, w_packed, bias, out, o_bias=None):
     """x [H,W,Cin] view, o [H,W,>=432] view (raw conv_offset.6 output; its bias may be passed as o_bias instead of being
-    pre-added), flow [H,W,2]|None, out [H,W,128] view (all pixel-major).  4-D tensors [n,H,W,.] run the batched entry."""
-    if x.dim() == 4:
-        n, H, W, Cin = x.shape
-        xp, ldx = _pm(x)
-        op, ldo = _pm(o)
-        outp, ldout = _pm(out)
-        L = _lib.lib()
-        ws_bytes = L.pp_deform_align_batched_workspace_bytes(n, H, W)
-        ws = torch.empty(max(ws_bytes // 4, 4), device=x.device, dtype=torch.float32)
-        check(L.pp_deform_align_batched(xp, ldx, op, ldo, _p(o_bias), _p(_dense(flow)) if flow is not None else None, float(max_res),
-                                        _p(_dense(w_packed)), _p(bias), outp, ldout, n, H, W, Cin, out.shape[-1], _p(ws), ws_bytes,
-                                        _stream()), "pp_deform_align_batched")
-        _count(3)
-        return out
+    pre-added), flow [H,W,2]|None, out [H,W,128] view (all pixel-major).  The warp-level mma.sync implementation: kept as
+    the measured baseline of deform_gather + conv_umma (config.UMMA_CONV)."""
     H, W, Cin = x.shape
     xp, ldx = _pm(x)
     op, ldo = _pm(o)
@@ -227,18 +215,47 @@ def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pr
     return out
 
 
-def deform_gather(x, o, flow, max_res, cols=None, o_bias=None):
-    """x [n,H,W,Cin] view, o [n,H,W,>=432] raw conv_offset output, flow [n,H,W,2] | None -> cols [n,H,W,9*Cin]
-    (modulated bilinear samples, k*Cin + c, TF32-rounded): the A operand of the deformable conv's GEMM."""
+def deform_gather(x, o, flow, max_res, cols=None, o_bias=None, x2=None):
+    """x [n,H,W,Cin] view (or, with x2, the two halves x | x2 of Cin/2 channels each), o [n,H,W,>=432] raw conv_offset
+    output, flow [n,H,W,2] | None -> cols [n,H,W,9*Cin] (modulated bilinear samples, k*Cin + c, TF32-rounded): the A
+    operand of the deformable conv's GEMM."""
     n, H, W, Cin = x.shape
     xp, ldx = _pm4(x)
+    x2p, ldx2 = (None, 0)
+    if x2 is not None:
+        if x2.shape != x.shape:
+            raise RuntimeError("deform_gather: x2 must have the shape of x")
+        x2p, ldx2 = _pm4(x2)
+        Cin *= 2
     op, ldo = _pm4(o)
     if cols is None:
         cols = torch.empty(n, H, W, 9 * Cin, device=x.device, dtype=torch.float32)
-    check(_lib.lib().pp_deform_gather(xp, ldx, op, ldo, _p(o_bias), _p(_dense(flow)) if flow is not None else None, float(max_res),
-                                      _p(_dense(cols)), n, H, W, Cin, _stream()), "pp_deform_gather")
+    check(_lib.lib().pp_deform_gather(xp, ldx, x2p, ldx2, op, ldo, _p(o_bias), _p(_dense(flow)) if flow is not None else None,
+                                      float(max_res), _p(_dense(cols)), n, H, W, Cin, _stream()), "pp_deform_gather")
     _count(1)
     return cols
+
+
+def flow_warp_fbcheck(feat, fprop, fcheck=None, warped=None, aux=None, want_warp=True, round_tf32=False):
+    """flow_warp (bilinear) of pixel-major maps feat [n,h,w,C] by fprop [n,h,w,2] -> warped [n,h,w,C] (views allowed);
+    with fcheck also the forward-backward validity: aux [n,h,w,>=3] view receives (fx, fy, valid).  Returns (warped, aux)."""
+    n, h, w = fprop.shape[:3]
+    fp_, ldf, wp_, ldw, C = None, 0, None, 0, 0
+    if want_warp:
+        C = feat.shape[-1]
+        if warped is None:
+            warped = torch.empty(n, h, w, C, device=feat.device, dtype=torch.float32)
+        fp_, ldf = _pm4(feat)
+        wp_, ldw = _pm4(warped)
+    ap, lda = (None, 0)
+    if fcheck is not None:
+        if aux is None:
+            aux = torch.empty(n, h, w, 4, device=fprop.device, dtype=torch.float32)
+        ap, lda = _pm4(aux)
+    check(_lib.lib().pp_flow_warp_fbcheck(fp_, ldf, _p(_dense(fprop)), _p(_dense(fcheck)) if fcheck is not None else None, wp_, ldw,
+                                          ap, lda, n, h, w, C, int(bool(round_tf32)), _stream()), "pp_flow_warp_fbcheck")
+    _count(1)
+    return warped, aux
 
 
 def pack_deform_weight_umma(weight):
@@ -288,6 +305,8 @@ def sparse_window_attn(qkv, pool_kv, key_tok, flags, t, NT, kf_start, kf_step, o
     prm.t, prm.NT, prm.WN, prm.NKO, prm.NP, prm.C = t, NT, WN, key_tok.shape[1], pool_kv.shape[1], C
     prm.kf_start, prm.kf_step = kf_start, kf_step
     prm.nkf = len(range(kf_start, t, kf_step))
+    if prm.nkf == 0:
+        out.zero_()                 # empty key set: masked windows yield zeros (softmax over an empty dim), see the C entry
     prm.scale_log2 = LOG2E / math.sqrt(128.0)
     for tns, dt in ((qkv, torch.float32), (pool_kv, torch.float32), (key_tok, torch.int32), (flags, torch.int32)):
         _p(_dense(tns), dt)

@@ -14,6 +14,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "shipping: run with the default (benchmarked) precision switches")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device and the built library: skip (not fail) them where either is missing."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    lib = os.path.join(ROOT, "propainter_b200", "libpropainter_b200.so")
+    if have and os.path.exists(lib):
+        return
+    why = "no CUDA device" if not have else "libpropainter_b200.so not built"
+    skip = pytest.mark.skip(reason=f"gpu test: {why}")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def hostsim():
     """ctypes handle to the host build of pp_elem.cuh (test harness, see tests/hostsim/hostsim.cpp)."""

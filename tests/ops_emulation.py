@@ -202,6 +202,70 @@ def install(monkeypatch, hostsim):
         hostsim.hs_upsample2x(_fp(x_pm), _fp(out), n, h, w, C)
         return out
 
+    def tf32_round(w):
+        return w                                           # plumbing is checked in exact fp32; the rounding itself is a GPU-test matter
+
+    def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pre=None, res=None, post_relu=False, out=None,
+                  round_tf32=False, bn=0, tile_w=0):
+        """unpacks the [Cout][K] weight layout of pp_conv2d_umma (include/propainter_b200.h) back to [Cout,Cin,KH,KW]"""
+        chans = [sg.shape[-1] for sg in segs]
+        nblk = sum((c + 31) // 32 for c in chans)
+        assert tuple(w_packed.shape) == (Cout, nblk * KH * KW * 32)
+        wb = w_packed.view(Cout, nblk, KH, KW, 32)
+        parts, b = [], 0
+        for c in chans:
+            for c0 in range(0, c, 32):
+                cw = min(32, c - c0)
+                assert wb[:, b, :, :, cw:].abs().max().item() == 0 if cw < 32 else True      # padded channels carry zero weights
+                parts.append(wb[:, b, :, :, :cw].permute(0, 3, 1, 2))
+                b += 1
+        w = torch.cat(parts, 1)
+        x = torch.cat(list(segs), -1).permute(0, 3, 1, 2)
+        t = F.conv2d(x, w, bias, padding=(KH // 2, KW // 2)).permute(0, 2, 3, 1)
+        if pre is not None:
+            t = t + pre
+        t = F.leaky_relu(t, slope) if act == "leaky" else _act[act](t)
+        if res is not None:
+            t = t + res
+        if post_relu:
+            t = F.relu(t)
+        if out is None:
+            return t.contiguous()
+        out.copy_(t)
+        return out
+
+    def deform_gather(x, o, flow, max_res, cols=None, o_bias=None, x2=None):
+        if x2 is not None:
+            x = torch.cat([x, x2], -1)
+        n, H, W, Cin = x.shape
+        if o_bias is not None:
+            o = o + o_bias
+        if cols is None:
+            cols = torch.empty(n, H, W, 9 * Cin)
+        for i in range(n):
+            xi, oi = x[i].contiguous(), o[i].contiguous()
+            ci = torch.empty(H * W, 9 * Cin)
+            hostsim.hs_deform_cols(_fp(xi), Cin, _fp(oi), oi.shape[-1], _fp(flow[i].contiguous()) if flow is not None else None,
+                                   ctypes.c_float(max_res), _fp(ci), H, W, Cin)
+            cols[i].copy_(ci.view(H, W, -1))
+        return cols
+
+    def flow_warp_fbcheck(feat, fprop, fcheck=None, warped=None, aux=None, want_warp=True, round_tf32=False):
+        from oracle import ops_ref
+        if want_warp:
+            wv = ops_ref.flow_warp(feat.permute(0, 3, 1, 2), fprop, "bilinear").permute(0, 2, 3, 1)
+            if warped is None:
+                warped = wv.contiguous()
+            else:
+                warped.copy_(wv)
+        if fcheck is not None:
+            valid = ops_ref.fb_consistency(fprop.permute(0, 3, 1, 2), fcheck.permute(0, 3, 1, 2))
+            if aux is None:
+                aux = torch.zeros(*fprop.shape[:3], 4)
+            aux[..., 0:2] = fprop
+            aux[..., 2] = valid[:, 0]
+        return warped, aux
+
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name) and not name.startswith("_"):
             monkeypatch.setattr(ops, name, fn)

@@ -181,6 +181,110 @@ def test_deform_align():
         assert (out2.cpu().permute(2, 0, 1) - ref).abs().max().item() < 2e-3 * scale
 
 
+def test_conv_umma_matches_torch_conv():
+    """pp_conv2d_umma (tcgen05 implicit GEMM, TMA-staged shifted halo boxes) vs F.conv2d in fp32.  `exact`: operands that are
+    exactly representable in TF32, so every product is exact and only the fp32 accumulation order differs (1e-5 of the
+    output scale: any indexing / swizzle / segment-order mistake is O(1)); `plain`: arbitrary fp32 activations reach the
+    tensor core truncated to TF32 (1.5e-3 of the output scale)."""
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    cases = [  # n, H, W, segment channels, Cout, KH, KW, act, pre, res, post_relu, bn, tile_w
+        (1, 30, 54, [128], 128, 3, 3, "leaky", True, True, False, 0, 0),          # flow-completion step conv
+        (1, 60, 108, [128], 432, 3, 3, "none", False, False, False, 0, 0),        # conv_offset.6 (ragged last N tile)
+        (2, 30, 54, [128, 128], 128, 3, 3, "leaky", True, False, False, 64, 16),  # two state segments, 8x16 tiles
+        (3, 17, 23, [128, 5], 36, 3, 3, "relu", False, True, True, 32, 0),        # ragged map, 5-channel segment, Cout < BN
+        (1, 60, 108, [264], 128, 3, 3, "sigmoid", False, False, False, 128, 0),   # channels not a multiple of 32
+        (1, 30, 54, [2304], 128, 1, 1, "none", False, False, False, 0, 0),        # deformable-conv GEMM over sampled columns
+        (2, 30, 54, [256], 128, 1, 5, "tanh", False, False, False, 0, 0),         # SepConvGRU shapes
+        (2, 30, 54, [256], 128, 5, 1, "none", False, False, False, 0, 0),
+    ]
+    for (n, H, W, segC, Cout, KH, KW, act, use_pre, use_res, post_relu, bn, tile_w) in cases:
+        Cin = sum(segC)
+        w = torch.randn(Cout, Cin, KH, KW, generator=gen) / (Cin * KH * KW) ** 0.5
+        b = torch.randn(Cout, generator=gen)
+        bufs = [torch.randn(n, H, W, C + 8, generator=gen).to(DEV) for C in segC]      # segments = channel slices of wider buffers
+        pre = torch.randn(n, H, W, Cout + 4, generator=gen).to(DEV)[..., :Cout] if use_pre else None
+        res = torch.randn(n, H, W, Cout + 8, generator=gen).to(DEV)[..., 4:4 + Cout] if use_res else None
+        for mode, tol in (("exact", 1e-5), ("plain", 1.5e-3)):
+            if mode == "exact":
+                xs = [ops.tf32_round(bf)[..., 4:4 + C] for bf, C in zip(bufs, segC)]
+                wr = ops.tf32_round(w)
+            else:
+                xs, wr = [bf[..., 4:4 + C] for bf, C in zip(bufs, segC)], w
+            outbuf = torch.zeros(n, H, W, Cout + 12, device=DEV)
+            out = outbuf[..., 8:8 + Cout]
+            ops.conv_umma(xs, ops.pack_conv_weight(wr, segC).to(DEV), KH, KW, Cout, bias=b.to(DEV), act=act, slope=0.1, pre=pre, res=res,
+                          post_relu=post_relu, out=out, bn=bn, tile_w=tile_w)
+            ref = F.conv2d(torch.cat(xs, -1).permute(0, 3, 1, 2), wr.to(DEV), b.to(DEV), padding=(KH // 2, KW // 2)).permute(0, 2, 3, 1)
+            if pre is not None:
+                ref = ref + pre
+            ref = {"none": lambda v: v, "relu": torch.relu, "leaky": lambda v: F.leaky_relu(v, 0.1), "sigmoid": torch.sigmoid,
+                   "tanh": torch.tanh}[act](ref)
+            if res is not None:
+                ref = ref + res
+            if post_relu:
+                ref = torch.relu(ref)
+            err = ((out - ref).abs().max() / ref.abs().max()).item()
+            assert err < tol, (mode, n, H, W, segC, Cout, KH, KW, err)
+            assert (outbuf[..., :8] == 0).all() and (outbuf[..., 8 + Cout:] == 0).all()      # nothing written outside the slice
+    # round_tf32: stored activations are TF32 values (the next conv's operands are then round-to-nearest, not truncated)
+    x = torch.randn(1, 16, 8, 32, generator=gen).to(DEV)
+    w = torch.randn(32, 32, 3, 3, generator=gen) * 0.1
+    y = ops.conv_umma([x], ops.pack_conv_weight(w).to(DEV), 3, 3, 32, round_tf32=True)
+    assert torch.equal(y, ops.tf32_round(y))
+    with pytest.raises(RuntimeError):
+        ops.conv_umma([x[..., :30]], ops.pack_conv_weight(w).to(DEV), 3, 3, 32)                # packed weight / segment mismatch
+
+
+def test_deform_gather_plus_gemm():
+    """pp_deform_gather + 1x1 pp_conv2d_umma = torchvision.ops.deform_conv2d as DeformableAlignment /
+    SecondOrderDeformableAlignment call it (same cases as test_deform_align, plus the split two-state input)."""
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    for Cin, use_flow, max_res, (H, W), split in ((128, True, 3.0, (60, 108), False), (256, False, 5.0, (30, 54), True),
+                                                  (256, False, 5.0, (30, 54), False), (128, True, 3.0, (7, 10), False)):
+        x = torch.randn(2, Cin, H, W, generator=gen)
+        o = torch.randn(2, 432, H, W, generator=gen) * 1.5
+        flow = torch.randn(2, 2, H, W, generator=gen) * 2
+        wgt = torch.randn(128, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+        bias, ob = torch.randn(128, generator=gen), torch.randn(432, generator=gen) * 0.3
+        o1, o2, m = torch.chunk(o, 3, dim=1)
+        offset = max_res * torch.tanh(torch.cat((o1, o2), 1))
+        if use_flow:
+            offset = offset + flow.flip(1).repeat(1, 144, 1, 1)
+        ref = ops_ref.deform_conv3x3(x, offset, torch.sigmoid(m), wgt, bias).permute(0, 2, 3, 1)
+        xp = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        op = (o.permute(0, 2, 3, 1) - ob).contiguous().to(DEV)
+        fl = flow.permute(0, 2, 3, 1).contiguous().to(DEV) if use_flow else None
+        if split:
+            a, b = xp[..., :Cin // 2].contiguous(), xp[..., Cin // 2:].contiguous()
+            cols = ops.deform_gather(a, op, fl, max_res, o_bias=ob.to(DEV), x2=b)
+        else:
+            cols = ops.deform_gather(xp, op, fl, max_res, o_bias=ob.to(DEV))
+        out = ops.conv_umma([cols], ops.pack_deform_weight_umma(wgt).to(DEV), 1, 1, 128, bias=bias.to(DEV))
+        scale = ref.abs().max().item()
+        assert (out.cpu() - ref).abs().max().item() < 2e-3 * scale, ((out.cpu() - ref).abs().max().item(), scale)
+
+
+def test_flow_warp_fbcheck():
+    from propainter_b200 import ops
+    gen = torch.Generator().manual_seed(6)
+    n, h, w, C = 3, 30, 54, 128
+    feat = torch.randn(n, h, w, C, generator=gen)
+    f1 = smooth_flow(gen, n, h * 8, w * 8, 3.0)[:, :, ::8, ::8].contiguous()
+    f2 = (-f1 + 0.4 * torch.randn(n, 2, h, w, generator=gen)).contiguous()
+    ref_w = ops_ref.flow_warp(feat.permute(0, 3, 1, 2), f1.permute(0, 2, 3, 1)).permute(0, 2, 3, 1)
+    ref_v = ops_ref.fb_consistency(f1, f2)[:, 0]
+    aux = torch.zeros(n, h, w, 8, device=DEV)
+    warped, _ = ops.flow_warp_fbcheck(feat.to(DEV), f1.permute(0, 2, 3, 1).contiguous().to(DEV), f2.permute(0, 2, 3, 1).contiguous().to(DEV),
+                                      aux=aux[..., :3])
+    assert (warped.cpu() - ref_w).abs().max() < 1e-5
+    assert torch.equal(aux[..., :2].cpu(), f1.permute(0, 2, 3, 1)) and (aux[..., 3:] == 0).all()
+    assert 0.05 < ref_v.mean() < 0.95 and (aux[..., 2].cpu() != ref_v).float().mean() < 2e-3
+    w2, none = ops.flow_warp_fbcheck(feat.to(DEV), f1.permute(0, 2, 3, 1).contiguous().to(DEV), round_tf32=True)
+    assert none is None and torch.equal(w2, ops.tf32_round(warped))
+
+
 def test_sparse_window_attention():
     """Attention core vs the oracle's window_attention with identity-free weights: we feed q/k/v projections
     computed by torch on the device and compare the pre-`proj` output through the oracle's own formula."""

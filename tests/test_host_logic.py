@@ -96,7 +96,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         getattr(handle, name)
-    assert _lib.lib().pp_abi_version() == 1
+    assert _lib.lib().pp_abi_version() == 2
     assert _lib.lib().pp_error_string(-3) == b"workspace too small"
     assert _lib.lib().pp_img_prop_scan_workspace_bytes(3, 4, 5) == 3 * 4 * 4 * 5 * 4
 
@@ -115,7 +115,7 @@ def test_ctypes_table_matches_header_prototypes():
     def ctype(decl):
         decl = decl.strip()
         if "*" in decl:
-            for struct in ("PPAttnParams", "PPWindowIds"):
+            for struct in ("PPAttnParams", "PPWindowIds", "PPConvParams"):
                 if struct in decl:
                     return ctypes.POINTER(getattr(_lib, struct))
             return ctypes.c_char_p if decl.replace("const", "").strip().startswith("char") and "(" not in decl and decl.count(" ") <= 1 else ctypes.c_void_p

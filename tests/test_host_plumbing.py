@@ -47,9 +47,9 @@ def test_flow_completion_plumbing(emu):
     assert rel_err(pred[0], ref[0]) < 1e-4 and rel_err(pred[1], ref[1]) < 1e-4, (rel_err(pred[0], ref[0]), rel_err(pred[1], ref[1]))
 
 
-def test_flow_completion_batched_directions(emu, monkeypatch):
-    """config.RFC_BATCHED: the forward- and backward-flow nets as one batch of two (clip-major stacking, per-clip temporal
-    taps in the P3D blocks, batched deform-align) must give what the two independent runs give."""
+def test_flow_completion_both_conv_plans(emu, monkeypatch):
+    """config.UMMA_CONV on (segmented inputs, hoisted frame-only conv shares, gather + 1x1 GEMM) and off (cuDNN convs +
+    concat buffers + pp_deform_align) are two execution plans of the same scan: both must match the oracle."""
     from propainter_b200 import config
     from propainter_b200.model.recurrent_flow_completion import RecurrentFlowCompleteNet
     net = RecurrentFlowCompleteNet(None, seed=2)
@@ -57,18 +57,22 @@ def test_flow_completion_batched_directions(emu, monkeypatch):
     flows = (torch.randn(1, 5, 2, 32, 48, generator=gen), torch.randn(1, 5, 2, 32, 48, generator=gen))
     masks = torch.zeros(1, 6, 1, 32, 48)
     masks[..., 8:24, 12:36] = 1
-    sep, _ = net.forward_bidirect_flow(flows, masks)
-    monkeypatch.setattr(config, "RFC_BATCHED", True)
-    bat, _ = net.forward_bidirect_flow(flows, masks)
     ref = flowcomp_ref.forward_bidirect_flow(net.state_dict(), flows, masks)
-    for k in (0, 1):
-        assert rel_err(bat[k], ref[k]) < 1e-4 and rel_err(bat[k], sep[k]) < 1e-5, (rel_err(bat[k], ref[k]), rel_err(bat[k], sep[k]))
+    for flag in (True, False):
+        monkeypatch.setattr(config, "UMMA_CONV", flag)
+        out, _ = net.forward_bidirect_flow(flows, masks)
+        for k in (0, 1):
+            assert rel_err(out[k], ref[k]) < 1e-4, (flag, k, rel_err(out[k], ref[k]))
 
 
-@pytest.mark.parametrize("H,W,t,lt,alt", [(64, 96, 4, 3, False), (128, 128, 3, 2, False), (64, 64, 2, 1, False), (64, 96, 4, 3, True)])
+@pytest.mark.parametrize("H,W,t,lt,alt", [(64, 96, 4, 3, False), (128, 128, 3, 2, False), (64, 64, 2, 1, False), (64, 96, 4, 3, True),
+                                          (64, 96, 4, 3, "cudnn"), (64, 64, 2, 1, "cudnn")])
 def test_generator_plumbing(emu, monkeypatch, H, W, t, lt, alt):
-    from propainter_b200 import autotune
+    from propainter_b200 import autotune, config
     from propainter_b200.model.propainter import InpaintGenerator
+    if alt == "cudnn":                                  # the library-conv plan of the propagation scan (config.UMMA_CONV off)
+        monkeypatch.setattr(config, "UMMA_CONV", False)
+        alt = False
     if alt:      # force the alternative execution plans autotune may pick on the GPU (per-group dense encoder convs)
         monkeypatch.setattr(autotune, "pick", lambda key, variants, *a, **k: variants[0 if key[0] == "conv_relu" else -1](*a))
     net = InpaintGenerator(seed=3)
