@@ -317,12 +317,17 @@ def run_ours(args, wl):
         runner = ShardedProPainter(pipe)
 
     def step_resident():
-        return runner(u8_dev, fm_dev, md_dev, cfg)
+        r = runner(u8_dev, fm_dev, md_dev, cfg)
+        return r[0] if shard else r
 
     def step_e2e():
-        comp = runner(u8_host, fm_host, md_host, cfg)          # H2D inside
-        out_host.copy_(comp, non_blocking=True)                # D2H of the result
-        return comp
+        r = runner(u8_host, fm_host, md_host, cfg)             # H2D inside
+        if shard:                                              # every rank reads back the frames whose final value it holds
+            comp, ids = r
+            out_host[:comp.shape[0]].copy_(comp, non_blocking=True)
+            return comp
+        out_host.copy_(r, non_blocking=True)                   # D2H of the result
+        return r
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):

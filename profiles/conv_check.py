@@ -49,7 +49,7 @@ def main(group):
         w = torch.randn(Cout, Cin, KH, KW, device=dev) / (Cin * KH * KW) ** 0.5
         b = torch.randn(Cout, device=dev) if use_bias else None
         # segments live as channel slices of wider buffers (like the scan buffers of the product)
-        bufs = [torch.randn(n, H, W, C + 8, device=dev) for C in segC]
+        bufs = [torch.randn(n, H, W, (C + 11) // 4 * 4, device=dev) for C in segC]   # pixel stride: multiple of 16 bytes
         pre = torch.randn(n, H, W, Cout + 4, device=dev)[..., :Cout] if use_pre else None
         res = torch.randn(n, H, W, Cout + 8, device=dev)[..., 4:4 + Cout] if use_res else None
         outbuf = torch.zeros(n, H, W, Cout + 12, device=dev)

@@ -197,53 +197,63 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     }
     if (lane == 0) { CV_PROF(5, wa); CV_PROF(6, wb); CV_PROF(7, tfirst); CV_PROF(8, CV_CLK()); }
   } else {
-    // ================================================= epilogue: thread <-> TMEM lane <-> pixel of the tile
-    const int r = warp * 32 + lane;
-    const int y = y0 + r / p.BW, x = x0 + r % p.BW;
-    const bool valid = y < p.H && x < p.W;
-    const long pix = ((long)img * p.H + y) * p.W + x;
+    // ================================================= epilogue.  tcgen05.ld hands every thread one accumulator row (TMEM lane =
+    // pixel) x 32 columns; storing that way makes each warp instruction touch 32 different 128-byte lines (measured: ~2.2 k
+    // cycles of LSU wavefronts per 32 columns, and the same again for each of pre / res).  The rows therefore go through a
+    // 32 x 36-float staging tile per warp (the operand ring is idle by now) and the bias / pre / activation / residual math
+    // runs in the transposed mapping lane <-> (row = 4i + lane/8, 4 columns = lane%8): 8 lanes cover one pixel's 128 bytes,
+    // so every global load and store instruction moves four full lines.
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float* stg = reinterpret_cast<float*>(sA) + warp * (32 * 36);
+    const int rsub = lane >> 3, c4 = lane & 7;
     const float* __restrict__ bias = p.bias;
-    const float* __restrict__ pre = p.pre ? p.pre + pix * p.ld_pre + n0 : nullptr;
-    const float* __restrict__ res = p.res ? p.res + pix * p.ld_res + n0 : nullptr;
-    float* __restrict__ orow = p.out + pix * p.ld_out + n0;
     const int act = p.act, post_relu = p.post_relu, round_tf32 = p.round_tf32;
     const float slope = p.slope;
+    long pixi[8];                                                   // pixel index of row 4i + rsub of this warp's 32 rows (-1: outside the map)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 32 + 4 * i + rsub;
+      const int y = y0 + r / p.BW, x = x0 + r % p.BW;
+      pixi[i] = (y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
+    }
     ua_bar_wait(bar(32), 0);
     if (tid == 0) CV_PROF(9, CV_CLK());
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t v[32];
       UA_LD32(tD + c0 + lane_off, v);
-      // all global loads of the chunk are issued before anything is stored (they would otherwise serialise behind the
-      // stores, one L2 round trip per float4: ~5.5 k cycles per 32 columns measured)
-      float4 bv[8], pv[8], rv[8];
+      const int n = n0 + c0 + 4 * c4;
+      const bool n_in = n < p.Cout;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), pv[8], rv[8];
+      if (bias && n_in) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const bool in = n0 + c0 + 4 * c < p.Cout;
-        bv[c] = (bias && in) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        pv[c] = (pre && in && valid) ? *reinterpret_cast<const float4*>(pre + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rv[c] = (res && in && valid) ? *reinterpret_cast<const float4*>(res + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const bool on = n_in && pixi[i] >= 0;
+        pv[i] = (p.pre && on) ? *reinterpret_cast<const float4*>(p.pre + pixi[i] * p.ld_pre + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rv[i] = (p.res && on) ? *reinterpret_cast<const float4*>(p.res + pixi[i] * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (n0 + c0 + 4 * c < p.Cout) {
-            float4 a = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                                   __uint_as_float(v[4 * c + 3]));
-            a.x += bv[c].x + pv[c].x; a.y += bv[c].y + pv[c].y; a.z += bv[c].z + pv[c].z; a.w += bv[c].w + pv[c].w;
-            if (act) { a.x = cv_act(a.x, act, slope); a.y = cv_act(a.y, act, slope); a.z = cv_act(a.z, act, slope); a.w = cv_act(a.w, act, slope); }
-            a.x += rv[c].x; a.y += rv[c].y; a.z += rv[c].z; a.w += rv[c].w;
-            if (post_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-            if (round_tf32) {
-              a.x = __uint_as_float(pp_tf32(a.x)); a.y = __uint_as_float(pp_tf32(a.y));
-              a.z = __uint_as_float(pp_tf32(a.z)); a.w = __uint_as_float(pp_tf32(a.w));
-            }
-            *reinterpret_cast<float4*>(orow + c0 + 4 * c) = a;
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
+        if (n_in && pixi[i] >= 0) {
+          a.x += bv.x + pv[i].x; a.y += bv.y + pv[i].y; a.z += bv.z + pv[i].z; a.w += bv.w + pv[i].w;
+          if (act) { a.x = cv_act(a.x, act, slope); a.y = cv_act(a.y, act, slope); a.z = cv_act(a.z, act, slope); a.w = cv_act(a.w, act, slope); }
+          a.x += rv[i].x; a.y += rv[i].y; a.z += rv[i].z; a.w += rv[i].w;
+          if (post_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+          if (round_tf32) {
+            a.x = __uint_as_float(pp_tf32(a.x)); a.y = __uint_as_float(pp_tf32(a.y));
+            a.z = __uint_as_float(pp_tf32(a.z)); a.w = __uint_as_float(pp_tf32(a.w));
           }
+          *reinterpret_cast<float4*>(p.out + pixi[i] * p.ld_out + n) = a;
         }
       }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -378,26 +388,32 @@ extern "C" int pp_conv2d_umma(const PPConvParams* q, cudaStream_t stream) {
 // model/recurrent_flow_completion.py:31-44): decode the raw conv_offset output (max_res*tanh offsets (+ flow.flip),
 // sigmoid modulation), sample x bilinearly at the 9 x 16 positions of every pixel and write the modulated samples as
 // columns cols[p][k*Cin + c] (rounded to TF32: they are the A operand of the GEMM that follows = pp_conv2d_umma with a
-// 1x1 kernel over `cols`).  One warp per (pixel, tap): lane <-> (group, half of the group's channels), so a warp reads
+// 1x1 kernel over `cols`).  One warp per pixel: lane <-> (group, half of the group's channels), so per tap a warp reads
 // 16 positions x 4 corners x 32/64 B and writes one contiguous Cin*4-byte run.
 template <int CPL>   // channels per lane: 4 (Cin = 128) or 8 (Cin = 256)
 __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__ x, int ld_x, const float* __restrict__ x2, int ld_x2,
     const float* __restrict__ o, int ld_o,
     const float* __restrict__ obias, const float* __restrict__ flow, float max_res, float* __restrict__ cols, long npix, int H, int W) {
-  const long item = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (item >= npix * 9) return;
+  // One warp per pixel, lane <-> (offset group g, half of the group's channels).  The 27 offset-net outputs of (pixel, g)
+  // are fetched up front, then the 9 taps run in batches of 3 with all 12 (24) corner loads of a batch in flight before
+  // the first one is used: the kernel is latency-bound (two dependent memory round trips per tap), so what matters is
+  // how many independent loads each warp keeps outstanding.
+  const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= npix) return;
   const int lane = threadIdx.x & 31, g = lane >> 1, half = lane & 1;
-  const long pix = item / 9; const int k = (int)(item - pix * 9);
   const long HW = (long)H * W, img = pix / HW, pim = pix - img * HW;
   const int y = (int)(pim / W), xx = (int)(pim - (long)y * W);
   const float* op = o + pix * ld_o;
-  float oy = op[g * 18 + 2 * k], ox = op[g * 18 + 2 * k + 1], ml = op[288 + g * 9 + k];
-  if (obias) { oy += obias[g * 18 + 2 * k]; ox += obias[g * 18 + 2 * k + 1]; ml += obias[288 + g * 9 + k]; }
-  oy = max_res * tanhf(oy); ox = max_res * tanhf(ox);
-  if (flow) { oy += flow[2 * pix + 1]; ox += flow[2 * pix]; }
-  PPDTap t; t.py = (float)(y - 1 + k / 3) + oy; t.px = (float)(xx - 1 + k % 3) + ox; t.m = 1.0f / (1.0f + expf(-ml));
-  const PPDW d = pp_deform_weights(t, H, W);
-  constexpr int CIN = CPL * 32;
+  float2 off[9]; float ml[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { off[k] = *reinterpret_cast<const float2*>(op + g * 18 + 2 * k); ml[k] = op[288 + g * 9 + k]; }
+  float fy = 0.f, fx = 0.f;
+  if (flow) { fx = flow[2 * pix]; fy = flow[2 * pix + 1]; }
+  if (obias) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { off[k].x += obias[g * 18 + 2 * k]; off[k].y += obias[g * 18 + 2 * k + 1]; ml[k] += obias[288 + g * 9 + k]; }
+  }
+  constexpr int CIN = CPL * 32, NV = CPL / 4;
   const int c = g * (2 * CPL) + half * CPL;
   // x2 != NULL: the input channels are split over two maps of CIN/2 channels each (offset groups 0-7 | 8-15): the two
   // previous states of the second-order scan live in different slots of the history buffer (no torch.cat)
@@ -405,27 +421,44 @@ __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__
   if (second) { x = x2; ld_x = ld_x2; }
   const int cs = second ? c - CIN / 2 : c;
   const float* xi = x + img * HW * ld_x;
-  const float* p00 = xi + ((long)d.y0 * W + d.x0) * ld_x + cs;
-  const float wts[4] = {d.w00, d.w01, d.w10, d.w11};
-  const float* q[4] = {p00, p00 + ld_x, p00 + (long)W * ld_x, p00 + (long)W * ld_x + ld_x};
-  float4 acc[CPL / 4];
+  float* dst = cols + pix * (9L * CIN) + c;
 #pragma unroll
-  for (int i = 0; i < CPL / 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int kb = 0; kb < 9; kb += 3) {
+    float wts[3][4];
+    float4 v[3][4][NV];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float w = wts[j];
-    const float* a = w != 0.f ? q[j] : xi + cs;                   // never dereference an out-of-image corner
+    for (int u = 0; u < 3; ++u) {
+      const int k = kb + u;
+      PPDTap t;
+      t.py = (float)(y - 1 + k / 3) + (max_res * tanhf(off[k].x) + fy);      // same association as pp_deform_tap (pp_elem.cuh)
+      t.px = (float)(xx - 1 + k % 3) + (max_res * tanhf(off[k].y) + fx);
+      t.m = 1.0f / (1.0f + expf(-ml[k]));
+      const PPDW d = pp_deform_weights(t, H, W);
+      wts[u][0] = d.w00; wts[u][1] = d.w01; wts[u][2] = d.w10; wts[u][3] = d.w11;
+      const float* p00 = xi + ((long)d.y0 * W + d.x0) * ld_x + cs;
+      const float* q[4] = {p00, p00 + ld_x, p00 + (long)W * ld_x, p00 + (long)W * ld_x + ld_x};
 #pragma unroll
-    for (int i = 0; i < CPL / 4; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(a + 4 * i);
-      acc[i].x += v.x * w; acc[i].y += v.y * w; acc[i].z += v.z * w; acc[i].w += v.w * w;
+      for (int j = 0; j < 4; ++j) {
+        const float* a = wts[u][j] != 0.f ? q[j] : xi + cs;                // never dereference an out-of-image corner
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[u][j][i] = *reinterpret_cast<const float4*>(a + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float w = wts[u][j];
+          acc.x += v[u][j][i].x * w; acc.y += v[u][j][i].y * w; acc.z += v[u][j][i].z * w; acc.w += v[u][j][i].w * w;
+        }
+        *reinterpret_cast<float4*>(dst + (long)(kb + u) * CIN + 4 * i) =
+            make_float4(__uint_as_float(pp_tf32(acc.x)), __uint_as_float(pp_tf32(acc.y)), __uint_as_float(pp_tf32(acc.z)), __uint_as_float(pp_tf32(acc.w)));
+      }
     }
   }
-  float* dst = cols + pix * (9L * CIN) + (long)k * CIN + c;
-#pragma unroll
-  for (int i = 0; i < CPL / 4; ++i)
-    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(pp_tf32(acc[i].x)), __uint_as_float(pp_tf32(acc[i].y)),
-                                                          __uint_as_float(pp_tf32(acc[i].z)), __uint_as_float(pp_tf32(acc[i].w)));
 }
 
 extern "C" int pp_deform_gather(const float* x, int ld_x, const float* x2, int ld_x2, const float* o, int ld_o, const float* o_bias,
@@ -433,8 +466,9 @@ extern "C" int pp_deform_gather(const float* x, int ld_x, const float* x2, int l
   if ((Cin != 128 && Cin != 256) || n < 1 || H < 1 || W < 1) return PP_ERR_SHAPE;
   if (ld_x % 4 || ld_o < 432 || ((uintptr_t)x & 15) || ((uintptr_t)cols & 15)) return PP_ERR_ALIGN;
   if (x2 && (ld_x2 % 4 || ((uintptr_t)x2 & 15))) return PP_ERR_ALIGN;
+  if (ld_o % 2 || ((uintptr_t)o & 7)) return PP_ERR_ALIGN;           // (dy,dx) pairs are fetched as float2
   const long npix = (long)n * H * W;
-  const long blocks = (npix * 9 + 7) / 8;
+  const long blocks = (npix + 7) / 8;
   if (blocks > 0x7fffffffL) return PP_ERR_SHAPE;
   if (Cin == 128) k_deform_gather<4><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
   else k_deform_gather<8><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);

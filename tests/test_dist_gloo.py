@@ -39,7 +39,10 @@ def _worker(rank, world, port, T, sub, out_path):
     u8, fm, md = synth.make_clip(T, 128, 128, mask="ellipse", seed=0)
     pipe = ProPainterPipeline(device="cpu")                       # same seeds on every rank -> identical weights
     cfg = InferenceConfig(raft_iter=1, subvideo_length=sub)
-    sharded = ShardedProPainter(pipe)(torch.from_numpy(u8), fm, md, cfg)
+    sp = ShardedProPainter(pipe)
+    sharded = sp(torch.from_numpy(u8), fm, md, cfg, gather=True)
+    part, ids = sp(torch.from_numpy(u8), fm, md, cfg)            # the sharded result: this rank's final frames only
+    assert torch.equal(part, sharded[ids]) and sp.last_bytes.get('encoder_features', 0) >= 0
     if rank == 0:
         single = pipe(torch.from_numpy(u8), fm, md, cfg)
         np.savez(out_path, sharded=sharded.numpy(), single=single.numpy())
@@ -59,10 +62,36 @@ def test_partition_helpers():
         assert sorted(fin) == list(range(80)) and fin[0] == 0 and fin[79] == world - 1
 
 
-def test_sharded_pipeline_matches_single_process(tmp_path, hostsim):
-    """T=13 with subvideo_length=6: several units in every stage, windows split 2+1, a seam between the ranks."""
+@pytest.mark.parametrize("world,T,sub", [(2, 13, 6), (3, 17, 80)])
+def test_sharded_pipeline_matches_single_process(tmp_path, hostsim, world, T, sub):
+    """(2 ranks, T=13, subvideo_length=6): several units in every stage and a seam between the ranks; (3 ranks, T=17, one
+    sub-video): the two flow directions of the single completion unit run on different ranks, the middle rank both receives
+    and forwards seam frames.  Point-to-point exchanges only; the result must equal the single-process run bit for bit."""
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(2, _free_port(), 13, 6, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), T, sub, out), nprocs=world, join=True)
     r = np.load(out)
-    assert r["sharded"].shape == (13, 128, 128, 3)
+    assert r["sharded"].shape == (T, 128, 128, 3)
     assert np.array_equal(r["sharded"], r["single"])
+
+
+def test_shard_plan_covers_everything():
+    """ShardPlan invariants for the benchmarked shapes (C2: 80 frames, C4: 300 frames) at 1/2/4/8 ranks."""
+    from propainter_b200.dist import ShardPlan
+    from propainter_b200.inference_propainter import InferenceConfig
+    for T in (80, 300, 13):
+        for world in (1, 2, 4, 8):
+            sp = ShardPlan(T, world, InferenceConfig())
+            assert sorted(set(sp.fown)) == list(range(min(world, T))) and sp.fown == sorted(sp.fown)
+            for d in (0, 1):
+                assert all(o is not None for o in sp.pred_owner[d])
+            assert all(o is not None for o in sp.upd_owner) and sorted(sp.final_owner) == list(range(T))
+            assert sp.win_owner == sorted(sp.win_owner)
+            need = sp.needs_enc()
+            # a rank's windows use its own frames, <= 5 neighbour frames per side and the strided reference frames only
+            for r in range(world):
+                own = [i for i in range(T) if sp.fown[i] == r]
+                if own and T == 300:
+                    ext = [i for i in need[r] if i < own[0] - 5 or i > own[-1] + 5]
+                    assert all(i % 5 == 0 for i in ext) and len(ext) <= 16, (world, r, ext)   # refs: mid +- 10k, mid a multiple of 5
+            if T == 300 and world == 8:                                   # 4 sub-videos x 2 directions = one task per rank
+                assert sorted(sp.s2_owner) == list(range(8))

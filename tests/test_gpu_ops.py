@@ -202,7 +202,7 @@ def test_conv_umma_matches_torch_conv():
         Cin = sum(segC)
         w = torch.randn(Cout, Cin, KH, KW, generator=gen) / (Cin * KH * KW) ** 0.5
         b = torch.randn(Cout, generator=gen)
-        bufs = [torch.randn(n, H, W, C + 8, generator=gen).to(DEV) for C in segC]      # segments = channel slices of wider buffers
+        bufs = [torch.randn(n, H, W, (C + 11) // 4 * 4, generator=gen).to(DEV) for C in segC]      # segments = channel slices of wider buffers
         pre = torch.randn(n, H, W, Cout + 4, generator=gen).to(DEV)[..., :Cout] if use_pre else None
         res = torch.randn(n, H, W, Cout + 8, generator=gen).to(DEV)[..., 4:4 + Cout] if use_res else None
         for mode, tol in (("exact", 1e-5), ("plain", 1.5e-3)):
