@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- frames/s of the ProPainter inference hot path on B200 (contract in the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1] [--no-cpu-baseline]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4|c5] [--no-cpu-baseline]
+                  [--no-gpu-reference] [--no-strong] [--shard]
 
 A "step" is one full pass of stages 1-4 (RAFT flow -> flow completion -> image propagation ->
 sliding-window generator + compositing) over one synthetic clip.  N=1 workload = BASELINE.json
@@ -10,7 +11,10 @@ subvideo_length=80, raft_iter=20, random-init weights.
   value : frames/s with the uint8 clip + masks already resident in HBM
   e2e   : frames/s through ProPainterPipeline.__call__ with pinned HOST buffers: H2D of the clip
           and masks and D2H of the composited uint8 video inside the timed region
-N>1: one clip per rank (clips are independent units; weak scaling, no data-path collective).
+N>1: one clip per rank (clips are independent units; weak scaling, no data-path collective) -> `value`; in addition the
+`strong` block times ONE 300-frame 1280x720 clip (BASELINE.json configs[3]) time-sharded over the N ranks by
+propainter_b200/dist.py (point-to-point halo exchange over NCCL), at every N including 1, so that strong scaling
+of the long-clip configuration can be read off the per-N lines.
 --impl reference: the oracle (CPU restatement of the reference's PyTorch path) on the host cores
 over a bounded sample of the same workload.
 """
@@ -31,7 +35,14 @@ WORKLOADS = {
     "c2": dict(T=80, H=240, W=432, mask="ellipse", raft_iter=20,
                name="C2: 80-frame 432x240 object-removal, neighbor_length=10 ref_stride=10 subvideo_length=80, fp32"),
     "c1": dict(T=8, H=128, W=128, mask="square", raft_iter=20, name="C1: 8-frame 128x128 square mask, fp32"),
+    "c3": dict(T=80, H=240, W=432, mask="border", raft_iter=20,
+               name="C3: 80-frame 432x240 video completion (25% border mask), fp32 storage"),
+    "c4": dict(T=300, H=720, W=1280, mask="ellipse", raft_iter=20,
+               name="C4: 300-frame 1280x720 object-removal, subvideo_length=80 ref_stride=10, fp32 storage"),
+    "c5": dict(T=1000, H=1080, W=1920, mask="border", raft_iter=20,
+               name="C5: 1000-frame 1920x1080 completion, subvideo_length=80, fp32 storage"),
 }
+STRONG_WORKLOAD = "c4"     # the long clip of BASELINE.json configs[3] that `strong` shards over the ranks
 CPU_SAMPLE_FRAMES = 6      # bounded sample of the same workload for the CPU arm (full clip ~ 10 min of CPU)
 
 
@@ -278,6 +289,50 @@ def roofline_probe(torch, pipe, wl):
     return primary
 
 
+def strong_block(torch, dist, pipe, dev, rank, world, steps=2, warmup=1):
+    """One long clip (STRONG_WORKLOAD) cooperatively: every rank holds the uint8 clip + masks, computes its shard of every
+    stage and exchanges halos point to point; device-timed, max over ranks.  world == 1: the plain single-GPU pipeline."""
+    from propainter_b200 import synth
+    from propainter_b200.inference_propainter import InferenceConfig
+    wl = WORKLOADS[STRONG_WORKLOAD]
+    u8_np, fm, md = synth.make_clip(wl["T"], wl["H"], wl["W"], mask=wl["mask"], seed=0)
+    u8, fm, md = torch.from_numpy(u8_np).to(dev), fm.to(dev), md.to(dev)
+    cfg = InferenceConfig(raft_iter=wl["raft_iter"])
+    if world > 1:
+        from propainter_b200.dist import ShardedProPainter
+        runner = ShardedProPainter(pipe)
+        step = lambda: runner(u8, fm, md, cfg)
+    else:
+        runner = None
+        step = lambda: pipe(u8, fm, md, cfg)
+    for _ in range(warmup):
+        step()
+    total = 0.0
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    t = torch.tensor([total], device=dev, dtype=torch.float64)
+    sent = torch.tensor([sum(runner.last_bytes.values()) if runner else 0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+    out = {"workload": wl["name"], "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "value": wl["T"] * steps / (t.item() * 1e-3), "unit": "frames/s", "ms_per_clip": t.item() / steps,
+           "p2p_bytes_per_clip": sent.item(),
+           "exchange": "batched point-to-point (NCCL send/recv) of raw / completed flows, propagated frames, encoder features of "
+                       "neighbour + reference frames, uint8 seam frames; no collective on the data path"}
+    if runner is not None and rank == 0:
+        out["p2p_bytes_rank0_by_stage"] = dict(runner.last_bytes)
+    return out
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -361,6 +416,14 @@ def run_ours(args, wl):
 
     ms_total, launches, clocks = timed(step_resident, args.steps, args.warmup, True)
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    strong = None
+    if not args.no_strong and not shard and args.workload == "c2":
+        try:
+            strong = strong_block(torch, dist, pipe, dev, rank, world)
+        except Exception as exc:                                   # never lose the headline line to the extra block
+            strong = {"error": repr(exc)}
+            if world > 1:
+                raise
     frames_total = wl["T"] * (1 if shard else world) * args.steps
     if rank == 0:
         line = {
@@ -387,6 +450,8 @@ def run_ours(args, wl):
                 line["roofline_" + o.pop("key")] = o
         except Exception as exc:                                   # never lose the headline line to the probe
             line["roofline"] = {"error": repr(exc)}
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_gpu_reference:
             try:                                                   # the >= 10x target's denominator, same box, same clip
                 torch.cuda.empty_cache()
@@ -410,6 +475,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the `strong` block (one 300-frame 720p clip sharded over the ranks)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the gpu_reference block (reference PyTorch-CUDA plan, ~10 s)")
     ap.add_argument("--windows-in-flight", type=int, default=0, help="override InferenceConfig.windows_in_flight")
     ap.add_argument("--shard", action="store_true", help="N>1: cooperate on ONE clip (strong scaling) instead of one clip per rank")

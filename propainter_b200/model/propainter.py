@@ -275,7 +275,23 @@ class InpaintGenerator(ParamNet):
                                              masks_updated[bi], lt, interpolation, t_dilation))
         return torch.stack(res, 0).view(b, lt, 3, H, W).to(masked_frames.dtype)
 
-    def _forward_features(self, enc, flows_f, flows_b, mi, mu, lt, interpolation, t_dilation):
+    @torch.no_grad()
+    def forward_parts(self, masked_frames, completed_flows, masks_in, masks_updated, num_local_frames, interpolation="bilinear",
+                      t_dilation=2):
+        """`forward` for one clip (b = 1), run eagerly, that also returns the intermediate tensors the oracle exposes
+        (oracle/generator_ref.generator_forward(return_parts=True)): the propagated local features, the tokens entering and
+        leaving the transformer and the features handed to the decoder -- so parity tests can localise an error instead of
+        only seeing it after the tanh."""
+        lt = num_local_frames
+        enc = self._encode_frames(masked_frames[0].contiguous().float(), masks_in[0].contiguous().float(),
+                                  masks_updated[0].contiguous().float())
+        parts = {}
+        out = self._forward_features(enc, completed_flows[0][0].contiguous().float(), completed_flows[1][0].contiguous().float(),
+                                     masks_in[0].contiguous().float(), masks_updated[0].contiguous().float(), lt, interpolation, t_dilation,
+                                     parts=parts)
+        return out.unsqueeze(0), parts
+
+    def _forward_features(self, enc, flows_f, flows_b, mi, mu, lt, interpolation, t_dilation, parts=None):
         """one window after the encoder; captured as one CUDA graph per shape signature."""
         h, w = enc.shape[-2:]
         dsf, dsb, pmask = ops.gen_prep(flows_f, flows_b, mi, mu, lt)
@@ -290,7 +306,9 @@ class InpaintGenerator(ParamNet):
         else:
             local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
         enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
-        tok = self.tx.soft_split(enc2)
-        tok = self.tx.run(tok, (h, w), flags, t_dilation)
+        tok_in = self.tx.soft_split(enc2)
+        tok = self.tx.run(tok_in, (h, w), flags, t_dilation)
         enc3 = self.tx.soft_comp(tok, (h, w), res=enc2)                          # trans_feat + enc_feat (:365-366)
+        if parts is not None:
+            parts.update(prop_feat=local.contiguous(), tokens_in=tok_in, tokens_out=tok, enc_out=enc3.contiguous())
         return torch.tanh(self._decoder(enc3[:lt])).contiguous()

@@ -95,10 +95,18 @@ def test_generator_matches_oracle(H, W, t, lt):
     upd = masks * (torch.rand(1, t, 1, H, W, generator=gen) > 0.5).float()
     mf = frames * (1 - masks)
     out = net(mf.to(DEV), (flows[0].to(DEV), flows[1].to(DEV)), masks.to(DEV), upd.to(DEV), lt)
-    ref = generator_ref.generator_forward(cpu_sd(net), mf, flows, masks, upd, lt)
+    ref, rparts = generator_ref.generator_forward(cpu_sd(net), mf, flows, masks, upd, lt, return_parts=True)
     e = rel_err(out.cpu(), ref)
-    print(f"generator {H}x{W}: rel {e:.2e}, out std {ref.std():.3f}")
-    assert out.shape == (1, lt, 3, H, W) and e < 2e-2
+    # intermediate tensors: localises an error to the propagation scan / the transformer / the decoder
+    out2, parts = net.forward_parts(mf.to(DEV), (flows[0].to(DEV), flows[1].to(DEV)), masks.to(DEV), upd.to(DEV), lt)
+    fh, fw = parts["tokens_in"].shape[1:3]
+    ep = {"prop_feat": rel_err(parts["prop_feat"].cpu(), rparts["prop_feat"][0]),
+          "tokens_in": rel_err(parts["tokens_in"].cpu(), rparts["tokens_in"].view(t, fh, fw, -1)),
+          "tokens_out": rel_err(parts["tokens_out"].cpu(), rparts["tokens_out"].view(t, fh, fw, -1)),
+          "enc_out": rel_err(parts["enc_out"].cpu(), rparts["enc_out"][0])}
+    print(f"generator {H}x{W}: rel {e:.2e}, out std {ref.std():.3f}; parts " + " ".join(f"{k}={v:.2e}" for k, v in ep.items()))
+    assert out.shape == (1, lt, 3, H, W) and e < 5e-3 and rel_err(out2.cpu(), ref) < 5e-3
+    assert ep["prop_feat"] < 5e-3 and ep["tokens_in"] < 5e-3 and ep["tokens_out"] < 5e-3 and ep["enc_out"] < 5e-3
 
 
 def test_generator_half_storage():
