@@ -196,6 +196,23 @@ int pp_upsample2x_bilinear(const float* src, float* dst, int n, int h, int w, in
 int pp_mask_dilate(const uint8_t* src, float* dst, int T, int H, int W, int iterations, cudaStream_t stream);
 /* to_tensors()(frames)*2-1  core/utils.py:130-170 + inference_propainter.py:264: uint8 [T][H][W][3] -> planar float */
 int pp_u8_to_frames(const uint8_t* src, float* dst, int T, int H, int W, cudaStream_t stream);
+/* ---- resizing around the path (inference_propainter.py:34-45 resize_frames, :95-96 mask resize, :469-470 output resize) --- */
+/* HOST helpers (no GPU work): the per-axis tables of the three library resamplers the reference calls.
+ * bicubic: Pillow's Image.resize(size) on 8-bit images (BICUBIC, 22-bit fixed point): bounds [out*2] = (first source index,
+ * taps), kk [out*ksize]; returns ksize (kk == NULL: query only) or < 0.  nearest: Pillow's Image.resize(size, NEAREST): source
+ * index per destination index.  linear_cv: OpenCV's 8-bit INTER_LINEAR: ofs [out], coef [out*2] (11-bit taps). */
+int pp_resample_coeffs_bicubic(int in_size, int out_size, int* bounds, int* kk, long kk_capacity);
+int pp_resample_index_nearest(int in_size, int out_size, int* idx);
+int pp_resample_coeffs_linear_cv(int in_size, int out_size, int horizontal, int* ofs, short* coef);
+/* Device passes; tables are device copies of the above.  uint8 [T][H][W][3] -> [T][Ho][Wo][3] (nearest: C channels). */
+size_t pp_resize_u8_bicubic_workspace_bytes(int T, int H, int Wo);
+int pp_resize_u8_bicubic(const uint8_t* src, uint8_t* dst, int T, int H, int W, int Ho, int Wo, const int* bounds_x, const int* kk_x,
+                         int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, void* workspace, size_t ws_bytes,
+                         cudaStream_t stream);
+int pp_resize_u8_nearest(const uint8_t* src, uint8_t* dst, int T, int H, int W, int Ho, int Wo, int C, const int* idx_x, const int* idx_y,
+                         cudaStream_t stream);
+int pp_resize_u8_bilinear_cv(const uint8_t* src, uint8_t* dst, int T, int H, int W, int Ho, int Wo, const int* xofs, const short* alpha,
+                             const int* yofs, const short* beta, cudaStream_t stream);
 #define PP_MAX_WINDOW 32
 typedef struct PPWindowIds { int n; int frame[PP_MAX_WINDOW]; int first[PP_MAX_WINDOW]; } PPWindowIds;
 /* inference_propainter.py:437-450: pred planar [n][3][H][W] in (-1,1), masks planar [T][1][H][W],

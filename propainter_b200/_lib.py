@@ -87,6 +87,15 @@ SIGNATURES = {
     "pp_upsample2x_bilinear": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pp_mask_dilate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pp_u8_to_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pp_resample_coeffs_bicubic": (c_int, [c_int, c_int, c_void_p, c_void_p, c_long]),
+    "pp_resample_index_nearest": (c_int, [c_int, c_int, c_void_p]),
+    "pp_resample_coeffs_linear_cv": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pp_resize_u8_bicubic_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pp_resize_u8_bicubic": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_int, c_void_p, c_size_t, c_void_p]),
+    "pp_resize_u8_nearest": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pp_resize_u8_bilinear_cv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p]),
     "pp_composite_blend_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(PPWindowIds), c_int, c_int,
                                       c_void_p]),
 }

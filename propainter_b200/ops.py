@@ -461,3 +461,81 @@ def composite_blend(pred, masks, ori_u8, comp_u8, frame_ids, first_flags):
                                            _p(_dense(comp_u8), torch.uint8), ctypes.byref(ids), H, W, _stream()),
           "pp_composite_blend_u8")
     _count(1)
+
+
+# ---------------------------------------------------------------- resizing around the path (tables on the host, passes on the device)
+_TABLES = {}
+
+
+def resample_tables(kind, in_size, out_size, device=None, horizontal=True):
+    """Per-axis tables of the library resamplers the reference calls (see include/propainter_b200.h), as torch tensors
+    (on `device` if given).  kind: "bicubic" -> (bounds int32 [out,2], kk int32 [out,ksize]); "nearest" -> idx int32 [out];
+    "linear_cv" -> (ofs int32 [out], coef int16 [out,2])."""
+    key = (kind, in_size, out_size, str(device), horizontal)
+    if key in _TABLES:
+        return _TABLES[key]
+    L = _lib.lib()
+    if kind == "bicubic":
+        ks = L.pp_resample_coeffs_bicubic(in_size, out_size, None, None, 0)
+        bounds, kk = torch.empty(out_size, 2, dtype=torch.int32), torch.empty(out_size, ks, dtype=torch.int32)
+        check(min(0, L.pp_resample_coeffs_bicubic(in_size, out_size, bounds.data_ptr(), kk.data_ptr(), kk.numel())), "pp_resample_coeffs_bicubic")
+        res = (bounds, kk)
+    elif kind == "nearest":
+        idx = torch.empty(out_size, dtype=torch.int32)
+        check(L.pp_resample_index_nearest(in_size, out_size, idx.data_ptr()), "pp_resample_index_nearest")
+        res = (idx,)
+    elif kind == "linear_cv":
+        ofs, coef = torch.empty(out_size, dtype=torch.int32), torch.empty(out_size, 2, dtype=torch.int16)
+        check(L.pp_resample_coeffs_linear_cv(in_size, out_size, int(bool(horizontal)), ofs.data_ptr(), coef.data_ptr()), "pp_resample_coeffs_linear_cv")
+        res = (ofs, coef)
+    else:
+        raise ValueError(kind)
+    if device is not None:
+        res = tuple(t.to(device) for t in res)
+    _TABLES[key] = res
+    return res
+
+
+def resize_frames_u8(frames_u8, size):
+    """resize_frames (inference_propainter.py:34-45): uint8 [T,H,W,3] -> [T,Ho,Wo,3], size = (Wo, Ho) like PIL; = PIL.Image.resize(size)."""
+    T, H, W, _ = frames_u8.shape
+    Wo, Ho = size
+    dev = frames_u8.device
+    bx, kx = resample_tables("bicubic", W, Wo, dev)
+    by, ky = resample_tables("bicubic", H, Ho, dev)
+    out = torch.empty(T, Ho, Wo, 3, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    nws = L.pp_resize_u8_bicubic_workspace_bytes(T, H, Wo)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+    check(L.pp_resize_u8_bicubic(_p(_dense(frames_u8), torch.uint8), _p(out, torch.uint8), T, H, W, Ho, Wo, _p(bx, torch.int32), _p(kx, torch.int32),
+                                 kx.shape[1], _p(by, torch.int32), _p(ky, torch.int32), ky.shape[1], _p(ws, torch.uint8), ws.numel(), _stream()),
+          "pp_resize_u8_bicubic")
+    _count(2)
+    return out
+
+
+def resize_masks_u8(masks_u8, size):
+    """mask_img.resize(size, Image.NEAREST) (inference_propainter.py:95-96): uint8 [T,H,W] -> [T,Ho,Wo]."""
+    T, H, W = masks_u8.shape
+    Wo, Ho = size
+    dev = masks_u8.device
+    (ix,), (iy,) = resample_tables("nearest", W, Wo, dev), resample_tables("nearest", H, Ho, dev)
+    out = torch.empty(T, Ho, Wo, dtype=torch.uint8, device=dev)
+    check(_lib.lib().pp_resize_u8_nearest(_p(_dense(masks_u8), torch.uint8), _p(out, torch.uint8), T, H, W, Ho, Wo, 1, _p(ix, torch.int32),
+                                          _p(iy, torch.int32), _stream()), "pp_resize_u8_nearest")
+    _count(1)
+    return out
+
+
+def resize_output_u8(frames_u8, size):
+    """cv2.resize(f, out_size) of the composited frames (inference_propainter.py:469-470): uint8 [T,H,W,3] -> [T,Ho,Wo,3]."""
+    T, H, W, _ = frames_u8.shape
+    Wo, Ho = size
+    dev = frames_u8.device
+    xo, xa = resample_tables("linear_cv", W, Wo, dev, True)
+    yo, ya = resample_tables("linear_cv", H, Ho, dev, False)
+    out = torch.empty(T, Ho, Wo, 3, dtype=torch.uint8, device=dev)
+    check(_lib.lib().pp_resize_u8_bilinear_cv(_p(_dense(frames_u8), torch.uint8), _p(out, torch.uint8), T, H, W, Ho, Wo, _p(xo, torch.int32),
+                                              _p(xa, torch.int16), _p(yo, torch.int32), _p(ya, torch.int16), _stream()), "pp_resize_u8_bilinear_cv")
+    _count(1)
+    return out

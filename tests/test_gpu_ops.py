@@ -480,3 +480,27 @@ def test_mask_dilate():
         ref = np.stack([scipy.ndimage.binary_dilation(m[i].numpy(), iterations=it) if it else m[i].numpy() > 0 for i in range(T)])
         out = ops.mask_dilate(m.to(DEV), it).cpu()[:, 0].numpy()
         assert np.array_equal(out > 0.5, ref) and set(np.unique(out)) <= {0.0, 1.0}
+
+
+def test_resize_kernels():
+    """Device resizing vs the host libraries the reference calls: PIL.Image.resize (BICUBIC default) for the frames,
+    Image.NEAREST for the masks, cv2.resize (INTER_LINEAR) for the output (inference_propainter.py:34-45, :95-96, :469-470)."""
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    from propainter_b200 import ops
+    rng = np.random.default_rng(0)
+    for (H, W, size) in ((243, 437, (432, 240)), (100, 150, (72, 48)), (37, 53, (160, 96)), (240, 432, (432, 240))):
+        fr = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+        got = ops.resize_frames_u8(torch.from_numpy(fr).to(DEV), size).cpu().numpy()
+        ref = np.stack([np.array(Image.fromarray(f, mode="RGB").resize(size)) for f in fr])
+        assert np.array_equal(got, ref), (H, W, size)
+        m = (rng.integers(0, 2, (2, H, W), dtype=np.uint8) * 255)
+        gm = ops.resize_masks_u8(torch.from_numpy(m).to(DEV), size).cpu().numpy()
+        rm = np.stack([np.array(Image.fromarray(x, mode="L").resize(size, Image.NEAREST)) for x in m])
+        assert np.array_equal(gm, rm)
+    for (H, W, size) in ((240, 432, (437, 243)), (64, 96, (101, 77)), (120, 200, (150, 90))):
+        fr = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        got = ops.resize_output_u8(torch.from_numpy(fr).to(DEV), size).cpu().numpy()
+        ref = np.stack([cv2.resize(f, size) for f in fr])
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
