@@ -22,6 +22,7 @@
 // Two rings: A (one slot per 32-channel block) and B (one slot per (block, dy) = KW taps).  mbarrier full/empty pairs,
 // tcgen05.commit releases slots.  Descriptor / instruction encodings: pp_umma.cuh (validated on B200, round 1).
 #include <cuda.h>
+#include <stdlib.h>
 #include "pp_elem.cuh"
 #include "pp_mma.cuh"
 #include "pp_umma.cuh"
@@ -117,6 +118,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tD = *tmem_base_p;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, parameter / descriptor fetch) touches no
+  // global memory and overlaps the tail of the previous kernel in the stream; the next kernel may start its own prologue
+  // now.  Global reads and writes below wait for the previous grid to have completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // The producer and MMA warps run their loops with all 32 lanes converged and hand single instructions to one elected
   // lane (elect.sync): TMA and tcgen05 instructions execute on the uniform datapath, and inside a divergent `if (lane == 0)`
@@ -262,6 +268,23 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tD), "r"(tmem_cols));
 }
 
+// launch with the programmatic-stream-serialization attribute (PDL); PP_PDL=0 in the environment falls back to plain launches
+static bool cv_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PP_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t cv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = cv_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 typedef CUresult (*PFN_cvEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -378,7 +401,7 @@ extern "C" int pp_conv2d_umma(const PPConvParams* q, cudaStream_t stream) {
   p.prof = g_cv_prof;
 #endif
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.n), (unsigned)((p.Cout + p.BN - 1) / p.BN));
-  k_conv_umma<<<grid, CV_THREADS, smem, stream>>>(p);
+  if (cv_launch(k_conv_umma, grid, dim3(CV_THREADS), (size_t)smem, stream, p) != cudaSuccess) return PP_ERR_LAUNCH;
   return cudaPeekAtLastError() == cudaSuccess ? PP_OK : PP_ERR_LAUNCH;
 }
 
@@ -398,6 +421,8 @@ __global__ void __launch_bounds__(256) k_deform_gather(const float* __restrict__
   // are fetched up front, then the 9 taps run in batches of 3 with all 12 (24) corner loads of a batch in flight before
   // the first one is used: the kernel is latency-bound (two dependent memory round trips per tap), so what matters is
   // how many independent loads each warp keeps outstanding.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // inputs come from the previous kernel in the stream (PDL)
   const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= npix) return;
   const int lane = threadIdx.x & 31, g = lane >> 1, half = lane & 1;
@@ -470,7 +495,9 @@ extern "C" int pp_deform_gather(const float* x, int ld_x, const float* x2, int l
   const long npix = (long)n * H * W;
   const long blocks = (npix + 7) / 8;
   if (blocks > 0x7fffffffL) return PP_ERR_SHAPE;
-  if (Cin == 128) k_deform_gather<4><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
-  else k_deform_gather<8><<<(unsigned)blocks, 256, 0, stream>>>(x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
+  cudaError_t e;
+  if (Cin == 128) e = cv_launch(k_deform_gather<4>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
+  else e = cv_launch(k_deform_gather<8>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ld_x, x2, ld_x2, o, ld_o, o_bias, flow, max_res, cols, npix, H, W);
+  if (e != cudaSuccess) return PP_ERR_LAUNCH;
   return cudaPeekAtLastError() == cudaSuccess ? PP_OK : PP_ERR_LAUNCH;
 }

@@ -1,5 +1,6 @@
 // HBM/L2-bound gather, stencil and elementwise kernels of the ProPainter hot path (sm_100a).
 // One thread (or one warp) per output element; the per-element rules live in pp_elem.cuh.
+#include <stdlib.h>
 #include "pp_elem.cuh"
 #include "pp_mma.cuh"
 #include "../../include/propainter_b200.h"
@@ -120,6 +121,8 @@ extern "C" int pp_prop_cond(const float* cur, int ld_cur, const float* prop, int
 __global__ void __launch_bounds__(256) k_flow_warp(long npix, int h, int w, int C, const float* __restrict__ feat, int ld_f,
     const float* __restrict__ fprop, const float* __restrict__ fcheck, float* __restrict__ warped, int ld_w,
     float* __restrict__ aux, int ld_a, int round_tf32) {
+  asm volatile("griddepcontrol.launch_dependents;");              // programmatic dependent launch (see conv_umma.cu)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
@@ -156,7 +159,15 @@ extern "C" int pp_flow_warp_fbcheck(const float* feat, int ld_f, const float* fp
   if (warped && (!feat || C % 4 || ld_f % 4 || ld_w % 4 || ((uintptr_t)feat & 15) || ((uintptr_t)warped & 15))) return PP_ERR_ALIGN;
   if (aux && (!fcheck || ld_a < 3)) return PP_ERR_SHAPE;
   const long npix = (long)n * h * w;
-  k_flow_warp<<<pp_blocks(npix, 8), 256, 0, stream>>>(npix, h, w, C, feat, ld_f, fprop, fcheck, warped, ld_w, aux, ld_a, round_tf32);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pp_blocks(npix, 8)); cfg.blockDim = dim3(256); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* env = getenv("PP_PDL");
+  cfg.attrs = attr; cfg.numAttrs = (env && env[0] == '0') ? 0 : 1;
+  if (cudaLaunchKernelEx(&cfg, k_flow_warp, npix, h, w, C, feat, ld_f, fprop, fcheck, warped, ld_w, aux, ld_a, round_tf32) != cudaSuccess)
+    return PP_ERR_LAUNCH;
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
