@@ -328,11 +328,18 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   p->tiles_x = (q->W + p->BW - 1) / p->BW; p->tiles_y = (q->H + p->BH - 1) / p->BH;
   const long tiles = (long)p->tiles_x * p->tiles_y * q->n;
   if (tiles > 0x7fffffffL) return PP_ERR_SHAPE;
-  // N tile: the largest of 128 / 64 / 32 that still gives the 148 SMs about one CTA each
+  // N tile.  Measured with the CV_PROFILE counters (profiles/conv_prof.py): one M=128 kind::tf32 MMA with both operands in
+  // shared memory costs ~85 + 0.23*N cycles (the 128 x 32-byte A slices are read at ~48 B/clk whatever N is), and a CTA
+  // runs K/8 of them back to back; CTAs beyond one per SM run as further waves.  Pick the N that minimises
+  // waves x (85 + 0.23 N); ties go to the larger tile (fewer re-reads of A from L2).
   int bn = q->bn;
   if (bn != 32 && bn != 64 && bn != 128) {
-    bn = 128;
-    while (bn > 32 && tiles * ((q->Cout + bn - 1) / bn) < 120) bn >>= 1;
+    long best = -1;
+    for (int cand = 128; cand >= 32; cand >>= 1) {
+      const long ctas = tiles * ((q->Cout + cand - 1) / cand), waves = (ctas + PP_NUM_SMS - 1) / PP_NUM_SMS;
+      const long cost = waves * (850 + 23 * cand / 10);
+      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
   }
   p->BN = bn;
   p->a_copy_bytes = (p->BH + p->KH - 1) * p->BW * 128;

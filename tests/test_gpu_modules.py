@@ -242,3 +242,33 @@ def test_pipeline_720p_and_border_mask():
         print(f"{W}x{H} T={T} mask={mask}: PSNR {psnr:.2f} dB vs oracle")
         assert psnr > 40.0
 
+
+
+@pytest.mark.shipping
+def test_proinpainter_wrapper_matches_host_pre_post_processing():
+    """ProInpainter.inpaint (web-demos/hugging_face/inpainter/base_inpainter.py:190-374) with frames whose size is not a
+    multiple of 8: device-side PIL-BICUBIC resize, NEAREST mask resize, dilation and cv2 output resize must give exactly what
+    the host libraries give around the same pipeline."""
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    import scipy.ndimage
+    from propainter_b200.inference_propainter import InferenceConfig
+    from propainter_b200.inpainter import ProInpainter, process_sizes
+    rng = np.random.default_rng(0)
+    T, H, W = 6, 139, 203
+    frames = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    masks = np.zeros((T, H, W), np.uint8)
+    masks[:, 40:90, 60:130] = 1
+    net = ProInpainter(device=DEV)
+    got = np.stack(net.inpaint(frames, masks, ratio=1.0, dilate_radius=4, raft_iter=2))
+    out_size, size = process_sizes((W, H), 1.0)
+    assert got.shape == (T, out_size[1], out_size[0], 3) and size == (200, 136) and out_size == (202, 138)
+    # the same through the host libraries the reference calls
+    fr = np.stack([np.array(Image.fromarray(f, mode="RGB").resize(size)) for f in frames])
+    mk = np.stack([np.array(Image.fromarray(m).resize(size, Image.NEAREST).convert("L")) for m in masks])
+    dil = np.stack([scipy.ndimage.binary_dilation(m, iterations=4).astype(np.float32) for m in mk])
+    md = torch.from_numpy(dil)[None, :, None]
+    comp = net.pipe(torch.from_numpy(fr), md, md.clone(), InferenceConfig(raft_iter=2)).cpu().numpy()
+    ref = np.stack([cv2.resize(f, out_size) for f in comp])
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
