@@ -263,14 +263,17 @@ class ShardedProPainter:
         comp = ori.new_zeros((len(touched), H, W, 3))
         visited = {f: False for f in touched}
         preds = {}
-        for wi in mine_w:
+
+        def job(wi):
             nb, refs = plan[wi]
             ids = nb + refs
-            preds[wi] = pipe.model.forward_features(
+            empty = like.new_empty(0, 2, H, W)
+            return lambda slot: pipe.model.forward_features(
                 self._stack(enc, ids).permute(0, 3, 1, 2),
-                (self._stack(pred[0], nb[:-1]) if len(nb) > 1 else like.new_empty(0, 2, H, W),
-                 self._stack(pred[1], nb[:-1]) if len(nb) > 1 else like.new_empty(0, 2, H, W)),
-                md_all[ids], self._stack(um1, ids), len(nb), slot=0)
+                (self._stack(pred[0], nb[:-1]) if len(nb) > 1 else empty, self._stack(pred[1], nb[:-1]) if len(nb) > 1 else empty),
+                md_all[ids], self._stack(um1, ids), len(nb), slot=slot)
+        # the window predictions do not depend on the seam: compute them all (several in flight), composite afterwards in order
+        pipe.run_windows([job(wi) for wi in mine_w], lambda k, p: preds.__setitem__(mine_w[k], p), cfg, ori.is_cuda)
         earlier = {f for wi in range(len(plan)) if owner[wi] < rank for f in plan[wi][0]}
         need = sorted(set(touched) & earlier)
         prev = max([owner[wi] for wi in range(len(plan)) if owner[wi] < rank], default=None)

@@ -166,44 +166,50 @@ class ProPainterPipeline:
         # encoder features depend only on (frame, mask, updated mask): computed once per clip, not once per window
         enc_all = self.model.encode(upd_frames[0], md, upd_masks[0]).permute(0, 2, 3, 1)     # pixel-major rows: cheap frame gather
         todo = [(wi, nb, refs) for wi, (nb, refs) in enumerate(plan) if windows is None or wi in windows]
-        nfl = max(1, int(cfg.windows_in_flight)) if upd_frames.is_cuda else 1
+
+        def job(nb, refs):
+            ids = nb + refs
+            return lambda slot: self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
+                                                            md[ids], upd_masks[0, ids], len(nb), slot=slot)
+
+        def consume(k, pred):
+            nb = todo[k][1]
+            ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
+            for i in nb:
+                visited[i] = True
+        self.run_windows([job(nb, refs) for _, nb, refs in todo], consume, cfg, upd_frames.is_cuda)
+        return comp
+
+    def run_windows(self, jobs, consume, cfg, cuda=True):
+        """Windows are independent given the stage-3 outputs: keep `cfg.windows_in_flight` of them in flight on side streams
+        (each slot owns its own captured graph instance); `consume(k, pred)` -- the compositing -- is replayed on the main stream
+        in ascending window order because the 1/2-1/2 blend of inference_propainter.py:445-450 is order-dependent.
+        jobs[k](slot) launches window k and returns its prediction."""
+        nfl = max(1, int(cfg.windows_in_flight)) if cuda else 1
         if nfl == 1:
-            for wi, nb, refs in todo:
-                ids = nb + refs
-                pred = self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
-                                                   md[ids], upd_masks[0, ids], len(nb))
-                ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
-                for i in nb:
-                    visited[i] = True
-            return comp
-        # windows are independent given the stage-3 outputs: keep `nfl` of them in flight on side streams (each slot owns
-        # its own captured graph instance); compositing is replayed on the main stream in ascending window order because
-        # the 1/2-1/2 blend of inference_propainter.py:445-450 is order-dependent
+            for k, jb in enumerate(jobs):
+                consume(k, jb(0))
+            return
         main = torch.cuda.current_stream()
         if not hasattr(self, "_side_streams") or len(self._side_streams) < nfl:
             self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(nfl)]
         pending = []
 
-        def drain(k):
-            while len(pending) > k:
-                slot, nb, pred = pending.pop(0)
+        def drain(keep):
+            while len(pending) > keep:
+                slot, k, pred = pending.pop(0)
                 main.wait_stream(self._side_streams[slot])
                 pred.record_stream(main)
-                ops.composite_blend(pred, md, ori_u8, comp, nb, [not visited[i] for i in nb])
-                for i in nb:
-                    visited[i] = True
-        for n, (wi, nb, refs) in enumerate(todo):
-            slot = n % nfl
+                consume(k, pred)
+        for k, jb in enumerate(jobs):
+            slot = k % nfl
             drain(nfl - 1)
-            ids = nb + refs
             st = self._side_streams[slot]
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                pred = self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
-                                                   md[ids], upd_masks[0, ids], len(nb), slot=slot)
-            pending.append((slot, nb, pred))
+                pred = jb(slot)
+            pending.append((slot, k, pred))
         drain(0)
-        return comp
 
     # ---- whole path
     @torch.no_grad()
