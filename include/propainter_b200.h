@@ -79,7 +79,7 @@ int pp_deform_align(const float* x, int ld_x, const float* o, int ld_o, const fl
  * w_packed: [Cout][K], K = KH*KW*sum_i roundup32(C_i); inside segment i, 32-channel block b (global block index blk):
  *   k = ((blk*KH + dy)*KW + dx)*32 + c   (c = channel - 32*b; padded channels hold zeros).  TF32 products, fp32 accumulate.
  * bias [Cout] | NULL; pre (pre-activation addend) / res (post-activation residual): pixel-major [n*H*W][ld] | NULL.
- * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh.  Cout % 4 == 0.  bn / tile_w: 0 = choose (see _plan). */
+ * act: 0 none, 1 relu, 2 leaky(slope), 3 sigmoid, 4 tanh.  Cout % 4 == 0.  bn / tile_w / tile_m: 0 = choose (see _plan). */
 #define PP_CONV_MAX_SEG 4
 typedef struct PPConvSeg { const float* x; int ld; int C; } PPConvSeg;
 typedef struct PPConvParams {
@@ -93,7 +93,7 @@ typedef struct PPConvParams {
   const float* res; int ld_res;
   float* out; int ld_out;
   int act; float slope; int post_relu; int round_tf32;
-  int bn, tile_w;
+  int bn, tile_w, tile_m;   /* tiling hints, 0 = choose: output channels per CTA (32|64|128), tile width (8|16), pixels per CTA (64|128) */
 } PPConvParams;
 int pp_conv2d_umma(const PPConvParams* prm, cudaStream_t stream);
 /* the tiling pp_conv2d_umma will use for `prm` (no launch): pixel tile, output-channel tile, CTA count, dynamic smem */

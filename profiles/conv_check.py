@@ -44,7 +44,7 @@ def main(group):
         return statistics.median(ts)
 
     def conv_case(name, n, H, W, segC, Cout, KH=3, KW=3, act="none", slope=0.1, use_bias=True, use_pre=False, use_res=False,
-                  post_relu=False, bn=0, tile_w=0, time_it=True, exact=True):
+                  post_relu=False, bn=0, tile_w=0, time_it=True, exact=True, tile_m=0):
         Cin = sum(segC)
         w = torch.randn(Cout, Cin, KH, KW, device=dev) / (Cin * KH * KW) ** 0.5
         b = torch.randn(Cout, device=dev) if use_bias else None
@@ -65,7 +65,7 @@ def main(group):
             wp = ops.pack_conv_weight(wr, segC)
             outbuf.zero_()
             ops.conv_umma(xs, wp, KH, KW, Cout, bias=b, act=act, slope=slope, pre=pre, res=res, post_relu=post_relu, out=out, bn=bn,
-                          tile_w=tile_w)
+                          tile_w=tile_w, tile_m=tile_m)
             torch.cuda.synchronize()
             xin = torch.cat(xs, -1).permute(0, 3, 1, 2)
             ref = F.conv2d(xin, wr, b, padding=(KH // 2, KW // 2)).permute(0, 2, 3, 1)
@@ -82,13 +82,13 @@ def main(group):
             pad_ok = outbuf[..., :8].abs().max().item() == 0 and outbuf[..., 8 + Cout:].abs().max().item() == 0
             if not pad_ok:
                 errs.append(float("nan"))
-        msg = f"{name:34s} n={n} {H}x{W} segC={segC} Cout={Cout} {KH}x{KW} act={act} bn={bn} tw={tile_w}: " + \
+        msg = f"{name:34s} n={n} {H}x{W} segC={segC} Cout={Cout} {KH}x{KW} act={act} bn={bn} tw={tile_w} tm={tile_m}: " + \
               " ".join(f"{m}={e:.2e}" for m, e in zip(("exact", "plain") if exact else ("plain",), errs))
         if time_it:
             xs = [bf[..., 4:4 + C] for bf, C in zip(bufs, segC)]
             wp = ops.pack_conv_weight(w, segC)
             t_own = timeit(lambda: ops.conv_umma(xs, wp, KH, KW, Cout, bias=b, act=act, slope=slope, pre=pre, res=res, post_relu=post_relu,
-                                                 out=out, bn=bn, tile_w=tile_w))
+                                                 out=out, bn=bn, tile_w=tile_w, tile_m=tile_m))
             torch.backends.cudnn.allow_tf32 = True
             xin = torch.cat(xs, -1).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
             wcl = w.contiguous(memory_format=torch.channels_last)
@@ -114,6 +114,12 @@ def main(group):
             conv_case(f"3x3 gen map bn={bn}", 1, 60, 108, [128], 128, bn=bn, exact=False)
         for bn in (32, 64, 128):
             conv_case(f"3x3 rfc map bn={bn}", 1, 30, 54, [128], 128, bn=bn, exact=False)
+        for bn in (32, 64, 128):
+            conv_case(f"3x3 gen map M=64 bn={bn}", 1, 60, 108, [128], 128, bn=bn, tile_m=64, exact=(bn == 128))
+        for bn in (32, 64, 128):
+            conv_case(f"3x3 rfc map M=64 bn={bn}", 1, 30, 54, [128], 128, bn=bn, tile_m=64, exact=(bn == 64))
+        conv_case("3x3 M=64 tile_w=16 leaky pre res", 2, 30, 54, [128, 128], 128, act="leaky", use_pre=True, use_res=True, tile_m=64, tile_w=16)
+        conv_case("1x1 M=64 K=1152", 1, 60, 108, [1152], 128, 1, 1, tile_m=64)
         conv_case("3x3 rfc map tile_w=16", 1, 30, 54, [128], 128, tile_w=16)
         conv_case("3x3 gen map tile_w=16", 1, 60, 108, [128], 128, tile_w=16)
         conv_case("3x3 3 segments", 1, 30, 54, [128, 128, 128], 128, act="leaky")

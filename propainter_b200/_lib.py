@@ -36,7 +36,7 @@ class PPConvParams(ctypes.Structure):
                 ("pre", c_void_p), ("ld_pre", c_int), ("res", c_void_p), ("ld_res", c_int),
                 ("out", c_void_p), ("ld_out", c_int),
                 ("act", c_int), ("slope", c_float), ("post_relu", c_int), ("round_tf32", c_int),
-                ("bn", c_int), ("tile_w", c_int)]
+                ("bn", c_int), ("tile_w", c_int), ("tile_m", c_int)]
 
 
 class PPWindowIds(ctypes.Structure):

@@ -38,9 +38,10 @@ struct alignas(64) CVParams {
   CUtensorMap tmB;
   int seg_blocks[PP_CONV_MAX_SEG];
   int nseg, nblk;
-  int n, H, W, KH, KW, BH, BW, BN;
+  int n, H, W, KH, KW, BH, BW, BN, M;    // M = BH*BW = 128 or 64 (UMMA M)
   int tiles_x, tiles_y;
   int na, nb;                 // ring depths
+  int ring_bytes;             // A ring + B ring, at least the 18 KB the epilogue staging tiles need
   int a_copy_bytes;           // (BH+KH-1)*BW*128
   int Cout;
   const float* bias; const float* pre; const float* res; float* out;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
   const int b_tap_bytes = p.BN * 128, b_slot_bytes = p.KW * b_tap_bytes;
   uint8_t* sA = base;
   uint8_t* sB = sA + p.na * a_slot_bytes;
-  uint8_t* tail = sB + p.nb * b_slot_bytes;
+  uint8_t* tail = base + p.ring_bytes;
   // barriers: [0,na) a_full  [8,8+na) a_empty  [16,16+nb) b_full  [24,24+nb) b_empty  32 acc_full
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tail);
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(tail + 40 * 8);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     if (lane == 0) { CV_PROF(1, wa); CV_PROF(2, wb); CV_PROF(3, CV_CLK()); }
   } else if (warp == 5) {
     // ================================================= MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(p.M >> 4) << 24);
     uint32_t acc = 0;
     long long wa = 0, wb = 0, t1, tfirst = 0;
     (void)wa; (void)wb; (void)t1; (void)tfirst;
@@ -215,12 +216,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     const float* __restrict__ bias = p.bias;
     const int act = p.act, post_relu = p.post_relu, round_tf32 = p.round_tf32;
     const float slope = p.slope;
-    long pixi[8];                                                   // pixel index of row 4i + rsub of this warp's 32 rows (-1: outside the map)
+    // M = 128: warp w's 32 TMEM lanes hold accumulator rows 32w .. 32w+31; M = 64: rows 16w .. 16w+15 in lanes 0-15 (the
+    // "half subpartition" layout of cta_group::1 M=64 accumulators, cute/atom/mma_traits_sm100.hpp), lanes 16-31 unused
+    const int rpw = p.M >> 2;
+    long pixi[8];                                                   // pixel index of row 4i + rsub of this warp's rows (-1: none / outside the map)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = warp * 32 + 4 * i + rsub;
+      const int rl = 4 * i + rsub, r = warp * rpw + rl;
       const int y = y0 + r / p.BW, x = x0 + r % p.BW;
-      pixi[i] = (y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
+      pixi[i] = (rl < rpw && y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
     }
     ua_bar_wait(bar(32), 0);
     if (tid == 0) CV_PROF(9, CV_CLK());
@@ -318,13 +322,16 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   if (q->res && (q->ld_res % 4 || ((uintptr_t)q->res & 15))) return PP_ERR_ALIGN;
   p->nseg = q->nseg; p->nblk = nblk;
   p->n = q->n; p->H = q->H; p->W = q->W; p->KH = q->KH; p->KW = q->KW;
-  // tile shape: 16x8 or 8x16 pixels, whichever wastes fewer padded pixels (ties: 16 rows x 8 columns)
+  // tile shape: (M/8) x 8 or (M/16) x 16 pixels, whichever wastes fewer padded pixels (ties: 8 columns)
   int bw = q->tile_w;
   if (bw != 8 && bw != 16) {
-    const long a8 = (long)((q->W + 7) / 8) * ((q->H + 15) / 16), a16 = (long)((q->W + 15) / 16) * ((q->H + 7) / 8);
+    const int mm = q->tile_m == 64 ? 64 : 128;
+    const long a8 = (long)((q->W + 7) / 8) * ((q->H + mm / 8 - 1) / (mm / 8)), a16 = (long)((q->W + 15) / 16) * ((q->H + mm / 16 - 1) / (mm / 16));
     bw = a16 < a8 ? 16 : 8;
   }
-  p->BW = bw; p->BH = 128 / bw;
+  const int M = q->tile_m == 64 ? 64 : 128;                      // UMMA M (pixels per CTA); 64 halves the per-MMA A traffic and the CTA's work
+  p->M = M;
+  p->BW = bw; p->BH = M / bw;
   p->tiles_x = (q->W + p->BW - 1) / p->BW; p->tiles_y = (q->H + p->BH - 1) / p->BH;
   const long tiles = (long)p->tiles_x * p->tiles_y * q->n;
   if (tiles > 0x7fffffffL) return PP_ERR_SHAPE;
@@ -354,7 +361,9 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   // spend what is left on more A slots (1x1 convs: deeper prefetch of the only large operand)
   while (na < CV_MAX_A_SLOTS && na < nblk && (na + 1) * a_slot + nb * b_slot <= CV_SMEM_BUDGET) ++na;
   p->na = na; p->nb = nb;
-  *smem_bytes = na * a_slot + nb * b_slot + 512 + 1024;
+  p->ring_bytes = na * a_slot + nb * b_slot;
+  if (p->ring_bytes < 4 * 32 * 36 * 4) p->ring_bytes = 4 * 32 * 36 * 4;
+  *smem_bytes = p->ring_bytes + 512 + 1024;
   p->Cout = q->Cout;
   p->bias = q->bias; p->pre = q->pre; p->res = q->res; p->out = q->out;
   p->ld_pre = q->ld_pre; p->ld_res = q->ld_res; p->ld_out = q->ld_out;

@@ -177,7 +177,7 @@ def _pm4(t):
 
 
 def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pre=None, res=None, post_relu=False, out=None,
-              round_tf32=False, bn=0, tile_w=0):
+              round_tf32=False, bn=0, tile_w=0, tile_m=0):
     """tcgen05 implicit-GEMM conv (stride 1, same padding) with fused epilogue.  segs: list of [n,H,W,C_i] pixel-major
     views = the channel-concatenated input; w_packed from pack_conv_weight(weight, [C_i...]); pre / res / out
     [n,H,W,Cout] views (channel slices of wider buffers allowed).  Returns out."""
@@ -209,7 +209,7 @@ def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pr
         setattr(prm, name, ptr.value)
         setattr(prm, "ld_" + name, ld)
     prm.act, prm.slope, prm.post_relu, prm.round_tf32 = ACT[act], float(slope), int(bool(post_relu)), int(bool(round_tf32))
-    prm.bn, prm.tile_w = int(bn), int(tile_w)
+    prm.bn, prm.tile_w, prm.tile_m = int(bn), int(tile_w), int(tile_m)
     check(_lib.lib().pp_conv2d_umma(ctypes.byref(prm), _stream()), "pp_conv2d_umma")
     _count(1)
     return out

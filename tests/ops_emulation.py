@@ -206,7 +206,7 @@ def install(monkeypatch, hostsim):
         return w                                           # plumbing is checked in exact fp32; the rounding itself is a GPU-test matter
 
     def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pre=None, res=None, post_relu=False, out=None,
-                  round_tf32=False, bn=0, tile_w=0):
+                  round_tf32=False, bn=0, tile_w=0, tile_m=0):
         """unpacks the [Cout][K] weight layout of pp_conv2d_umma (include/propainter_b200.h) back to [Cout,Cin,KH,KW]"""
         chans = [sg.shape[-1] for sg in segs]
         nblk = sum((c + 31) // 32 for c in chans)

@@ -188,7 +188,7 @@ def test_conv_umma_matches_torch_conv():
     tensor core truncated to TF32 (1.5e-3 of the output scale)."""
     from propainter_b200 import ops
     gen = torch.Generator().manual_seed(11)
-    cases = [  # n, H, W, segment channels, Cout, KH, KW, act, pre, res, post_relu, bn, tile_w
+    cases = [  # n, H, W, segment channels, Cout, KH, KW, act, pre, res, post_relu, bn, tile_w (negative: 64-pixel tiles of that width)
         (1, 30, 54, [128], 128, 3, 3, "leaky", True, True, False, 0, 0),          # flow-completion step conv
         (1, 60, 108, [128], 432, 3, 3, "none", False, False, False, 0, 0),        # conv_offset.6 (ragged last N tile)
         (2, 30, 54, [128, 128], 128, 3, 3, "leaky", True, False, False, 64, 16),  # two state segments, 8x16 tiles
@@ -197,6 +197,8 @@ def test_conv_umma_matches_torch_conv():
         (1, 30, 54, [2304], 128, 1, 1, "none", False, False, False, 0, 0),        # deformable-conv GEMM over sampled columns
         (2, 30, 54, [256], 128, 1, 5, "tanh", False, False, False, 0, 0),         # SepConvGRU shapes
         (2, 30, 54, [256], 128, 5, 1, "none", False, False, False, 0, 0),
+        (1, 30, 54, [128, 128], 128, 3, 3, "leaky", True, True, False, 64, -8),   # M = 64 tiles (8x8 pixels)
+        (2, 33, 21, [128], 432, 3, 3, "none", False, False, False, 128, -16),     # M = 64 tiles (4x16 pixels), ragged map
     ]
     for (n, H, W, segC, Cout, KH, KW, act, use_pre, use_res, post_relu, bn, tile_w) in cases:
         Cin = sum(segC)
@@ -214,7 +216,7 @@ def test_conv_umma_matches_torch_conv():
             outbuf = torch.zeros(n, H, W, Cout + 12, device=DEV)
             out = outbuf[..., 8:8 + Cout]
             ops.conv_umma(xs, ops.pack_conv_weight(wr, segC).to(DEV), KH, KW, Cout, bias=b.to(DEV), act=act, slope=0.1, pre=pre, res=res,
-                          post_relu=post_relu, out=out, bn=bn, tile_w=tile_w)
+                          post_relu=post_relu, out=out, bn=bn, tile_w=abs(tile_w), tile_m=64 if tile_w < 0 else 0)
             ref = F.conv2d(torch.cat(xs, -1).permute(0, 3, 1, 2), wr.to(DEV), b.to(DEV), padding=(KH // 2, KW // 2)).permute(0, 2, 3, 1)
             if pre is not None:
                 ref = ref + pre
