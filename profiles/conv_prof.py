@@ -22,14 +22,14 @@ buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
 setbuf(ctypes.c_void_p(buf.data_ptr()))
 
 
-def case(name, n, H, W, Cin, Cout, KH, KW, bn=0):
+def case(name, n, H, W, Cin, Cout, KH, KW, bn=0, tile_m=0):
     x = torch.randn(n, H, W, Cin, device=dev)
     w = torch.randn(Cout, Cin, KH, KW, device=dev) * 0.05
     wp = ops.pack_conv_weight(w)
     out = torch.empty(n, H, W, Cout, device=dev)
     for _ in range(3):
         buf.zero_()
-        ops.conv_umma([x], wp, KH, KW, Cout, out=out, bn=bn)
+        ops.conv_umma([x], wp, KH, KW, Cout, out=out, bn=bn, tile_m=tile_m)
         torch.cuda.synchronize()
     b = buf.view(-1, 16).cpu()
     b = b[b[:, 10] != 0]
@@ -45,5 +45,9 @@ case("3x3 rfc 128->128 auto", 1, 30, 54, 128, 128, 3, 3)
 case("3x3 gen 128->128 bn64", 1, 60, 108, 128, 128, 3, 3, 64)
 case("3x3 gen 128->128 bn128", 1, 60, 108, 128, 128, 3, 3, 128)
 case("1x1 gen K=1152 auto", 1, 60, 108, 1152, 128, 1, 1)
+case("3x3 gen 128->128 M=64 bn128", 1, 60, 108, 128, 128, 3, 3, 128, 64)
+case("3x3 gen 128->128 M=64 bn64", 1, 60, 108, 128, 128, 3, 3, 64, 64)
+case("3x3 rfc 128->128 M=64 bn64", 1, 30, 54, 128, 128, 3, 3, 64, 64)
+case("3x3 rfc 128->128 M=64 bn32", 1, 30, 54, 128, 128, 3, 3, 32, 64)
 case("1x1 tiny K=128", 1, 16, 8, 128, 32, 1, 1)
 case("3x3 tiny 32->32", 1, 16, 8, 32, 32, 3, 3)

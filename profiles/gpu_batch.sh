@@ -10,3 +10,5 @@ timeout 1500 python -m pytest tests/test_gpu_zz_full_size.py -q -m gpu -s > gpur
 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-strong > gpurun_out/bench_a.log 2> gpurun_out/bench_a.err
 timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-strong --no-gpu-reference --clips-in-flight 2 > gpurun_out/bench_b.log 2> gpurun_out/bench_b.err
 tail -3 gpurun_out/bench_a.log gpurun_out/bench_b.log
+PP_PDL=0 timeout 600 python -m pytest tests/test_gpu_modules.py -q -m gpu -k "flow_completion or generator_matches" > gpurun_out/pytest_nopdl.log 2>&1
+timeout 300 python profiles/ncu_targets.py --time > gpurun_out/kernel_times_r2.txt 2>&1

@@ -1,7 +1,7 @@
 """Launches the hot kernels once each at BASELINE configs[1] (C2, 432x240) shapes for ncu:
 
   ncu --set full --clock-control none --import-source on \
-      -k regex:'k_deform|k_sparse_attn|k_corr_lookup|k_inorm|k_add_layernorm|k_pool_depthwise|k_bias_act|k_gru' \
+      -k regex:'k_conv_umma|k_deform|k_flow_warp|k_sparse_attn|k_corr_lookup|k_inorm|k_add_layernorm|k_pool_depthwise|k_bias_act|k_gru' \
       -o gpurun_out/prof python profiles/ncu_targets.py          (then profiles/ncu_summarize.py on the report)
 
 and, with --time, prints CUDA-event timings of the same launches (never report numbers taken under ncu)."""
@@ -48,6 +48,28 @@ for tag, (H, W, Cin, use_flow, mr) in {"gen": (60, 108, 128, True, 3.0), "rfc": 
     b = torch.randn(128, device=dev)
     out = torch.empty(H, W, 128, device=dev)
     run(f"deform_align_{tag}", lambda: ops.deform_align(x, o, fl, mr, wp, b, out))
+
+# ---- tcgen05 conv kernel + deformable gather + flow warp at the two propagation-scan shapes
+for tag, (H, W) in {"gen": (60, 108), "rfc": (30, 54)}.items():
+    xc = torch.randn(1, H, W, 128, device=dev)
+    wpk = ops.pack_conv_weight(torch.randn(128, 128, 3, 3, device=dev) * 0.03)
+    bc, prec, resc = torch.randn(128, device=dev), torch.randn(1, H, W, 128, device=dev), torch.randn(1, H, W, 128, device=dev)
+    oc = torch.empty(1, H, W, 128, device=dev)
+    run(f"conv_umma_3x3_128_{tag}", lambda: ops.conv_umma([xc], wpk, 3, 3, 128, bias=bc, act="leaky", slope=0.1, pre=prec, res=resc, out=oc))
+    w432 = ops.pack_conv_weight(torch.randn(432, 128, 3, 3, device=dev) * 0.03)
+    o432 = torch.empty(1, H, W, 432, device=dev)
+    run(f"conv_umma_3x3_432_{tag}", lambda: ops.conv_umma([xc], w432, 3, 3, 432, out=o432))
+    cin = 128 if tag == "gen" else 256
+    xd = torch.randn(1, H, W, cin, device=dev)
+    od = torch.randn(1, H, W, 432, device=dev)
+    fld = torch.randn(1, H, W, 2, device=dev) if tag == "gen" else None
+    colsd = torch.empty(1, H, W, 9 * cin, device=dev)
+    run(f"deform_gather_{tag}", lambda: ops.deform_gather(xd, od, fld, 3.0 if tag == "gen" else 5.0, colsd))
+    wdp = ops.pack_deform_weight_umma(torch.randn(128, cin, 3, 3, device=dev) * 0.03)
+    run(f"conv_umma_1x1_deform_gemm_{tag}", lambda: ops.conv_umma([colsd], wdp, 1, 1, 128, bias=bc, out=oc))
+fw_feat, fw_flow = torch.randn(1, 60, 108, 128, device=dev), torch.randn(1, 60, 108, 2, device=dev)
+fw_out = torch.empty(1, 60, 108, 128, device=dev)
+run("flow_warp_gen", lambda: ops.flow_warp_fbcheck(fw_feat, fw_flow, warped=fw_out, round_tf32=True))
 
 # ---- sparse window attention: t=18 frames, 20x36 tokens, 5 of 16 windows masked (ellipse mask of C2), layer parity 0
 t, H2, W2, C = 18, 20, 36, 512
