@@ -11,18 +11,6 @@ import torch
 from . import config, ops
 
 
-_POOLS = {}
-
-
-def _shared_pool(device_index):
-    """One private memory pool per device shared by every captured graph (torch.cuda.graph(pool=...)): graphs are replayed
-    one stage after another (or on side streams that each own a distinct graph instance per slot), so their intermediates
-    can share blocks instead of every capture keeping its own pool for the lifetime of the cache."""
-    if device_index not in _POOLS:
-        _POOLS[device_index] = torch.cuda.graph_pool_handle()
-    return _POOLS[device_index]
-
-
 def _switches():
     """execution switches that are baked into a capture: part of the cache key, so flipping one re-captures"""
     return (config.LINEAR_TF32, config.FUSED_EPILOGUE, config.AUTOTUNE, config.CUDNN_BENCHMARK, config.UMMA_CONV,
@@ -30,15 +18,30 @@ def _switches():
 
 
 class GraphCache:
-    """max_entries bounds the number of live captures (least recently used is dropped; its memory returns to the pool)."""
+    """One cache per net.  max_entries bounds the number of live captures (least recently used is dropped).
+
+    Memory: captures made with the same `pool` id share one private memory pool (torch.cuda.graph(pool=...)), so the shape
+    signatures a net sees over a long clip (odd-length tail chunks, windows with different frame counts) reuse the same
+    blocks instead of each capture keeping its own pool for the lifetime of the cache.  Graphs that share a pool must never
+    be replayed concurrently: callers pass a distinct `pool` for every stream they replay on (the generator's windows in
+    flight use pool = slot), and pools are per cache, i.e. per net instance -- two pipelines working on different clips at the
+    same time (bench.py --clips-in-flight) never share one."""
 
     def __init__(self, enabled=True, warmup=2, max_entries=64):
         self.enabled, self.warmup, self.entries, self.max_entries = enabled, warmup, {}, max_entries
+        self.pools = {}
 
     def clear(self):
         self.entries = {}
+        self.pools = {}
 
-    def __call__(self, key, fn, *inputs):
+    def _pool(self, device_index, pool):
+        k = (device_index, pool)
+        if k not in self.pools:
+            self.pools[k] = torch.cuda.graph_pool_handle()
+        return self.pools[k]
+
+    def __call__(self, key, fn, *inputs, pool=0):
         """Run ``fn(*inputs)`` (tensors in, tensor / tuple of tensors out) through a captured graph.
         Returned tensors are fresh clones, so callers may keep them across replays."""
         if not (self.enabled and config.CUDA_GRAPHS) or not inputs[0].is_cuda:
@@ -61,7 +64,7 @@ class GraphCache:
             torch.cuda.synchronize()
             l0 = ops.LAUNCHES
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=_shared_pool(inputs[0].device.index)), config.cudnn_autotune():
+            with torch.cuda.graph(graph, pool=self._pool(inputs[0].device.index, pool)), config.cudnn_autotune():
                 out = fn(*static_in)
             e = (graph, static_in, out, ops.LAUNCHES - l0)
             ops.LAUNCHES = l0                                   # capture records launches, it does not run them
