@@ -18,30 +18,18 @@ def _switches():
 
 
 class GraphCache:
-    """One cache per net.  max_entries bounds the number of live captures (least recently used is dropped).
+    """One cache per net.  max_entries bounds the number of live captures (least recently used is dropped, its private
+    memory pool goes with it).  Every capture keeps its own memory pool: graphs that share a pool must never be replayed
+    concurrently, and several of ours are (windows in flight on side streams, the two flow directions, two pipelines
+    working on different clips) -- a shared pool was tried in round 2 and corrupted exactly those replays."""
 
-    Memory: captures made with the same `pool` id share one private memory pool (torch.cuda.graph(pool=...)), so the shape
-    signatures a net sees over a long clip (odd-length tail chunks, windows with different frame counts) reuse the same
-    blocks instead of each capture keeping its own pool for the lifetime of the cache.  Graphs that share a pool must never
-    be replayed concurrently: callers pass a distinct `pool` for every stream they replay on (the generator's windows in
-    flight use pool = slot), and pools are per cache, i.e. per net instance -- two pipelines working on different clips at the
-    same time (bench.py --clips-in-flight) never share one."""
-
-    def __init__(self, enabled=True, warmup=2, max_entries=64):
+    def __init__(self, enabled=True, warmup=2, max_entries=48):
         self.enabled, self.warmup, self.entries, self.max_entries = enabled, warmup, {}, max_entries
-        self.pools = {}
 
     def clear(self):
         self.entries = {}
-        self.pools = {}
 
-    def _pool(self, device_index, pool):
-        k = (device_index, pool)
-        if k not in self.pools:
-            self.pools[k] = torch.cuda.graph_pool_handle()
-        return self.pools[k]
-
-    def __call__(self, key, fn, *inputs, pool=0):
+    def __call__(self, key, fn, *inputs):
         """Run ``fn(*inputs)`` (tensors in, tensor / tuple of tensors out) through a captured graph.
         Returned tensors are fresh clones, so callers may keep them across replays."""
         if not (self.enabled and config.CUDA_GRAPHS) or not inputs[0].is_cuda:
@@ -64,7 +52,7 @@ class GraphCache:
             torch.cuda.synchronize()
             l0 = ops.LAUNCHES
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=self._pool(inputs[0].device.index, pool)), config.cudnn_autotune():
+            with torch.cuda.graph(graph), config.cudnn_autotune():
                 out = fn(*static_in)
             e = (graph, static_in, out, ops.LAUNCHES - l0)
             ops.LAUNCHES = l0                                   # capture records launches, it does not run them

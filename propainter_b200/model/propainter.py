@@ -257,7 +257,7 @@ class InpaintGenerator(ParamNet):
                            lambda *a: self._forward_features(*a, lt, interpolation, t_dilation),
                            enc_feat.contiguous(memory_format=torch.channels_last), completed_flows[0].contiguous().float(),
                            completed_flows[1].contiguous().float(), masks_in.contiguous().float(),
-                           masks_updated.contiguous().float(), pool=slot + 1)
+                           masks_updated.contiguous().float())
 
     @torch.no_grad()
     def forward(self, masked_frames, completed_flows, masks_in, masks_updated, num_local_frames,

