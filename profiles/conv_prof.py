@@ -38,7 +38,7 @@ def case(name, n, H, W, Cin, Cout, KH, KW, bn=0, tile_m=0):
     print(f"{name}: {b.shape[0]} CTAs | CTA lifetime {f(b[:, 10] - b[:, 0])} cyc | kernel span {int((b[:, 10].max() - t0))} cyc\n"
           f"   producer: wait a_empty {f(b[:, 1])}  wait b_empty {f(b[:, 2])}  done at +{f(b[:, 3] - b[:, 0])}\n"
           f"   mma     : wait a_full  {f(b[:, 5])}  wait b_full  {f(b[:, 6])}  first A at +{f(b[:, 7] - b[:, 4])}  loop end +{f(b[:, 8] - b[:, 4])}\n"
-          f"   epilogue: acc_full at +{f(b[:, 9] - b[:, 0])}  end +{f(b[:, 10] - b[:, 0])}", flush=True)
+          f"   epilogue: acc_full at +{f(b[:, 9] - b[:, 0])}  staged +{f(b[:, 12] - b[:, 9])}  stored +{f(b[:, 14] - b[:, 9])}  end(sync) +{f(b[:, 10] - b[:, 9])}", flush=True)
 
 
 case("3x3 rfc 128->128 auto", 1, 30, 54, 128, 128, 3, 3)

@@ -149,9 +149,92 @@ __global__ void __launch_bounds__(128) m64_layout(float* out) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(64));
 }
 
+// Epilogue timing: after one committed MMA, how long do (a) tcgen05.ld 32x32b.x32 + wait, (b) 8 STS.128 + syncwarp,
+// (c) 8 x (LDS.128 + STG.128) take for 4 warps?  Second round repeats (a)-(c) to separate one-time from steady costs.
+__global__ void __launch_bounds__(192) epi_probe(float* gout, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 64 * 1024 / 4; i += 192) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm(&tmem_base_s)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  if (warp == 5) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (elect()) {
+      for (int i = 0; i < 64; ++i)
+        asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                     ::"r"(tb), "l"(make_desc(sm(smem), 16, 1024, 2)), "l"(make_desc(sm(smem + 32 * 1024), 16, 1024, 2)), "r"(idesc), "r"(1u) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm(&bar)) : "memory");
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(sm(&bar)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    long long t[8];
+    t[0] = clock64();
+    for (int round = 0; round < 2; ++round) {
+      uint32_t v[32];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                     "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                     "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                   : "r"(tb + round * 32 + ((uint32_t)(warp * 32) << 16)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      t[1 + 3 * round] = clock64();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
+      t[2 + 3 * round] = clock64();
+      const int rsub = lane >> 3, c4 = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
+        *reinterpret_cast<float4*>(gout + ((long)(warp * 32 + 4 * i + rsub) * 128 + round * 32 + 4 * c4)) = a;
+      }
+      __syncwarp();
+      t[3 + 3 * round] = clock64();
+    }
+    if (tid == 0) for (int i = 0; i < 7; ++i) out[i] = t[i] - t[0];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(128));
+}
+
 int main() {
   long long* d;
-  cudaMalloc(&d, 16);
+  cudaMalloc(&d, 64);
+  {
+    float* go; long long h[8];
+    cudaMalloc(&go, 128 * 128 * 4);
+    cudaFuncSetAttribute(epi_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 2048);
+    for (int rep = 0; rep < 3; ++rep) {
+      epi_probe<<<1, 192, 64 * 1024 + 2048>>>(go, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("epi_probe: %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(h, d, 56, cudaMemcpyDeviceToHost);
+      printf("epilogue probe rep %d (cycles after acc_full): round0 tmem-ld %lld  staged %lld  stored %lld | round1 tmem-ld %lld staged %lld stored %lld\n",
+             rep, h[1], h[2], h[3], h[4], h[5], h[6]);
+    }
+    if (getenv("EPI_ONLY")) return 0;
+  }
   {
     float* o; float h[256];
     cudaMalloc(&o, 1024);

@@ -16,6 +16,7 @@ AUTOTUNE        time numerically equivalent plans of a step once per shape durin
                 conv-bias-ReLU.
 """
 import contextlib
+import os
 
 import torch
 
@@ -24,7 +25,7 @@ CUDNN_BENCHMARK = True
 CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
-UMMA_CONV = True
+UMMA_CONV = os.environ.get("PP_UMMA_CONV", "1") != "0"      # PP_UMMA_CONV=0: library convs + mma.sync deform kernel
 
 
 @contextlib.contextmanager

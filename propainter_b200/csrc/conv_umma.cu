@@ -41,7 +41,7 @@ struct alignas(64) CVParams {
   int n, H, W, KH, KW, BH, BW, BN, M;    // M = BH*BW = 128 or 64 (UMMA M)
   int tiles_x, tiles_y;
   int na, nb;                 // ring depths
-  int ring_bytes;             // A ring + B ring, at least the 18 KB the epilogue staging tiles need
+  int ring_bytes;             // A ring + B ring, at least what the epilogue staging tiles need (4 warps x BN/32 x 4.5 KB)
   int a_copy_bytes;           // (BH+KH-1)*BW*128
   int Cout;
   const float* bias; const float* pre; const float* res; float* out;
@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     // runs in the transposed mapping lane <-> (row = 4i + lane/8, 4 columns = lane%8): 8 lanes cover one pixel's 128 bytes,
     // so every global load and store instruction moves four full lines.
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    float* stg = reinterpret_cast<float*>(sA) + warp * (32 * 36);
     const int rsub = lane >> 3, c4 = lane & 7;
     const float* __restrict__ bias = p.bias;
     const int act = p.act, post_relu = p.post_relu, round_tf32 = p.round_tf32;
@@ -226,14 +225,31 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
       const int y = y0 + r / p.BW, x = x0 + r % p.BW;
       pixi[i] = (rl < rpw && y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
     }
+    const int nchunk = p.BN >> 5;
+    float* stgw = reinterpret_cast<float*>(sA) + warp * nchunk * (32 * 36);      // this warp's staging tiles, one per 32 columns
     ua_bar_wait(bar(32), 0);
     if (tid == 0) CV_PROF(9, CV_CLK());
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    // Phase A: all TMEM loads first.  tcgen05.wait::ld also waits for the thread's outstanding global stores (measured with
+    // profiles/probes/umma_rate_probe.cu: 55 cycles with nothing in flight, 150-900 right after a burst of STG), so a
+    // load -> store -> load -> store sequence pays one store round trip per 32 columns.
+    for (int ch = 0; ch < nchunk; ++ch) {
       uint32_t v[32];
-      UA_LD32(tD + c0 + lane_off, v);
-      const int n = n0 + c0 + 4 * c4;
+      UA_LD32(tD + ch * 32 + lane_off, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* stg = stgw + ch * (32 * 36);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    }
+    __syncwarp();
+    if (tid == 0) CV_PROF(12, CV_CLK());
+    // Phase B: bias / pre / activation / residual on the transposed mapping, coalesced loads and stores
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int n = n0 + ch * 32 + 4 * c4;
       const bool n_in = n < p.Cout;
+      const float* stg = stgw + ch * (32 * 36);
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), pv[8], rv[8];
       if (bias && n_in) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
 #pragma unroll
@@ -242,29 +258,32 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
         pv[i] = (p.pre && on) ? *reinterpret_cast<const float4*>(p.pre + pixi[i] * p.ld_pre + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         rv[i] = (p.res && on) ? *reinterpret_cast<const float4*>(p.res + pixi[i] * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the activation is selected once per chunk (warp-uniform branch), not per element: with the switch inside the
+      // element loop ptxas inlined the exp / tanh paths 32 times per chunk (~260 instructions between each shared-memory
+      // load and its global store; 3.8 k cycles per chunk measured)
+      auto finish = [&](auto actf) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
-            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
-        if (n_in && pixi[i] >= 0) {
-          a.x += bv.x + pv[i].x; a.y += bv.y + pv[i].y; a.z += bv.z + pv[i].z; a.w += bv.w + pv[i].w;
-          if (act) { a.x = cv_act(a.x, act, slope); a.y = cv_act(a.y, act, slope); a.z = cv_act(a.z, act, slope); a.w = cv_act(a.w, act, slope); }
-          a.x += rv[i].x; a.y += rv[i].y; a.z += rv[i].z; a.w += rv[i].w;
-          if (post_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-          if (round_tf32) {
-            a.x = __uint_as_float(pp_tf32(a.x)); a.y = __uint_as_float(pp_tf32(a.y));
-            a.z = __uint_as_float(pp_tf32(a.z)); a.w = __uint_as_float(pp_tf32(a.w));
+        for (int i = 0; i < 8; ++i) {
+          float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
+          if (n_in && pixi[i] >= 0) {
+            a.x = actf(a.x + (bv.x + pv[i].x)) + rv[i].x; a.y = actf(a.y + (bv.y + pv[i].y)) + rv[i].y;
+            a.z = actf(a.z + (bv.z + pv[i].z)) + rv[i].z; a.w = actf(a.w + (bv.w + pv[i].w)) + rv[i].w;
+            if (post_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+            if (round_tf32) {
+              a.x = __uint_as_float(pp_tf32(a.x)); a.y = __uint_as_float(pp_tf32(a.y));
+              a.z = __uint_as_float(pp_tf32(a.z)); a.w = __uint_as_float(pp_tf32(a.w));
+            }
+            *reinterpret_cast<float4*>(p.out + pixi[i] * p.ld_out + n) = a;
           }
-          *reinterpret_cast<float4*>(p.out + pixi[i] * p.ld_out + n) = a;
         }
-      }
-      __syncwarp();
+      };
+      if (act == 0) finish([](float v) { return v; });
+      else if (act == 1) finish([](float v) { return fmaxf(v, 0.f); });
+      else if (act == 2) finish([slope](float v) { return v > 0.f ? v : v * slope; });
+      else if (act == 3) finish([](float v) { return 1.0f / (1.0f + expf(-v)); });
+      else finish([](float v) { return tanhf(v); });
     }
+    if (tid == 0) CV_PROF(14, CV_CLK());
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -362,7 +381,7 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   while (na < CV_MAX_A_SLOTS && na < nblk && (na + 1) * a_slot + nb * b_slot <= CV_SMEM_BUDGET) ++na;
   p->na = na; p->nb = nb;
   p->ring_bytes = na * a_slot + nb * b_slot;
-  if (p->ring_bytes < 4 * 32 * 36 * 4) p->ring_bytes = 4 * 32 * 36 * 4;
+  if (p->ring_bytes < 4 * (bn / 32) * 32 * 36 * 4) p->ring_bytes = 4 * (bn / 32) * 32 * 36 * 4;   // epilogue staging tiles
   *smem_bytes = p->ring_bytes + 512 + 1024;
   p->Cout = q->Cout;
   p->bias = q->bias; p->pre = q->pre; p->res = q->res; p->out = q->out;
