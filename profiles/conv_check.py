@@ -128,6 +128,7 @@ def main(group):
         conv_case("3x3 ragged segs 128+5", 1, 60, 108, [128, 5], 128, act="leaky", use_pre=True)
         conv_case("3x3 Cout=432", 1, 60, 108, [128], 432)
         conv_case("3x3 Cout=432 rfc", 1, 30, 54, [128], 432)
+        conv_case("1x1 ragged segments 160+96", 1, 30, 54, [160, 96], 128, 1, 1, use_res=True)
         conv_case("1x1 K=1152 (deform gemm gen)", 1, 60, 108, [1152], 128, 1, 1)
         conv_case("1x1 K=2304 (deform gemm rfc)", 1, 30, 54, [2304], 128, 1, 1)
         conv_case("1x5 gru 256->256 n=8", 8, 30, 54, [256], 256, 1, 5)

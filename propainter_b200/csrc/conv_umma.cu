@@ -36,9 +36,11 @@
 struct alignas(64) CVParams {
   CUtensorMap tmA[PP_CONV_MAX_SEG];
   CUtensorMap tmB;
-  int seg_blocks[PP_CONV_MAX_SEG];
-  int nseg, nblk;
+  int seg_blocks[PP_CONV_MAX_SEG];   // pipeline blocks per segment (kgroup: groups of KW 32-channel blocks)
+  int seg_kblocks[PP_CONV_MAX_SEG];  // real 32-channel blocks per segment (= K extent of the segment / 32 per tap)
+  int nseg, nblk, kreal;      // nblk pipeline blocks; kreal real 32-channel blocks
   int n, H, W, KH, KW, BH, BW, BN, M;    // M = BH*BW = 128 or 64 (UMMA M)
+  int kgroup;                 // 1x1 convs: the `KW` loop walks `KW` consecutive 32-channel blocks (one pipeline stage = KW blocks)
   int tiles_x, tiles_y;
   int na, nb;                 // ring depths
   int ring_bytes;             // A ring + B ring, at least what the epilogue staging tiles need (4 warps x BN/32 x 4.5 KB)
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
   // registers (R2UR per operand) -- measured here at ~100 issue cycles per MMA against 32-64 cycles of tensor-pipe work.
   if (warp == 4) {
     // ================================================= TMA producer
-    int seg = 0, cb = 0;
+    int seg = 0, cb = 0, kbase = 0;                                  // kbase: first real k-block of the current segment
     long long wa = 0, wb = 0, t1;
     (void)wa; (void)wb; (void)t1;
     CV_PROF(0, CV_CLK());
@@ -143,8 +145,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
       if (ua_elect()) {
         cv_expect_tx(bar(sa), (uint32_t)a_slot_bytes);
         for (int dx = 0; dx < p.KW; ++dx)
-          cv_tma4(ua_smem(sA + sa * a_slot_bytes + dx * p.a_copy_bytes), &p.tmA[seg], cb * 32, x0 + dx - p.KW / 2,
-                  y0 - p.KH / 2, img, bar(sa));
+          if (p.kgroup)
+            cv_tma4(ua_smem(sA + sa * a_slot_bytes + dx * p.a_copy_bytes), &p.tmA[seg], (cb * p.KW + dx) * 32, x0, y0, img, bar(sa));
+          else
+            cv_tma4(ua_smem(sA + sa * a_slot_bytes + dx * p.a_copy_bytes), &p.tmA[seg], cb * 32, x0 + dx - p.KW / 2,
+                    y0 - p.KH / 2, img, bar(sa));
       }
       __syncwarp();
       for (int dy = 0; dy < p.KH; ++dy) {
@@ -155,11 +160,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
         if (ua_elect()) {
           cv_expect_tx(bar(16 + sb), (uint32_t)b_slot_bytes);
           for (int dx = 0; dx < p.KW; ++dx)
-            cv_tma2(ua_smem(sB + sb * b_slot_bytes + dx * b_tap_bytes), &p.tmB, (ib * p.KW + dx) * 32, n0, bar(16 + sb));
+            cv_tma2(ua_smem(sB + sb * b_slot_bytes + dx * b_tap_bytes), &p.tmB,
+                    (p.kgroup ? kbase + cb * p.KW + dx : ib * p.KW + dx) * 32, n0, bar(16 + sb));
         }
         __syncwarp();
       }
-      if (++cb == p.seg_blocks[seg]) { cb = 0; ++seg; }
+      if (++cb == p.seg_blocks[seg]) { cb = 0; kbase += p.seg_kblocks[seg]; ++seg; }
     }
     if (lane == 0) { CV_PROF(1, wa); CV_PROF(2, wb); CV_PROF(3, CV_CLK()); }
   } else if (warp == 5) {
@@ -328,11 +334,20 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   if (q->nseg < 1 || q->nseg > PP_CONV_MAX_SEG || q->n < 1 || q->H < 1 || q->W < 1) return PP_ERR_SHAPE;
   if (q->KH < 1 || q->KW < 1 || q->KH > 7 || q->KW > 7 || !(q->KH & 1) || !(q->KW & 1)) return PP_ERR_SHAPE;
   if (q->Cout < 4 || q->Cout % 4) return PP_ERR_SHAPE;
-  int nblk = 0;
+  int nblk = 0, kblocks = 0;
   for (int s = 0; s < q->nseg; ++s) {
     if (q->seg[s].C < 1) return PP_ERR_SHAPE;
     if (q->seg[s].ld % 4 || ((uintptr_t)q->seg[s].x & 15)) return PP_ERR_ALIGN;
-    p->seg_blocks[s] = (q->seg[s].C + 31) / 32;
+    p->seg_kblocks[s] = (q->seg[s].C + 31) / 32;
+    kblocks += p->seg_kblocks[s];
+  }
+  // 1x1 convs (plain GEMMs over the channels): a pipeline stage of one 32-channel block holds only 4 MMAs, and the fixed
+  // cost of a stage (barrier round trip, tcgen05 fence, commits: ~300-900 cycles measured) then exceeds the MMAs' own
+  // ~290 cycles.  Group 4 consecutive blocks per stage (the tap loop walks channels instead of x-shifts).
+  const int kv = (q->KH == 1 && q->KW == 1 && kblocks >= 8) ? 4 : 0;
+  p->kgroup = kv ? 1 : 0;
+  for (int s = 0; s < q->nseg; ++s) {
+    p->seg_blocks[s] = kv ? (p->seg_kblocks[s] + kv - 1) / kv : p->seg_kblocks[s];
     nblk += p->seg_blocks[s];
   }
   if (q->ld_out % 4 || ((uintptr_t)q->out & 15) || ((uintptr_t)q->w_packed & 15)) return PP_ERR_ALIGN;
@@ -340,7 +355,8 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   if (q->pre && (q->ld_pre % 4 || ((uintptr_t)q->pre & 15))) return PP_ERR_ALIGN;
   if (q->res && (q->ld_res % 4 || ((uintptr_t)q->res & 15))) return PP_ERR_ALIGN;
   p->nseg = q->nseg; p->nblk = nblk;
-  p->n = q->n; p->H = q->H; p->W = q->W; p->KH = q->KH; p->KW = q->KW;
+  p->n = q->n; p->H = q->H; p->W = q->W; p->KH = q->KH; p->KW = kv ? kv : q->KW;
+  p->kreal = kblocks;
   // tile shape: (M/8) x 8 or (M/16) x 16 pixels, whichever wastes fewer padded pixels (ties: 8 columns)
   int bw = q->tile_w;
   if (bw != 8 && bw != 16) {
@@ -370,7 +386,7 @@ static int cv_plan(const PPConvParams* q, CVParams* p, int* smem_bytes) {
   p->BN = bn;
   p->a_copy_bytes = (p->BH + p->KH - 1) * p->BW * 128;
   const int a_slot = p->KW * p->a_copy_bytes, b_slot = p->KW * bn * 128;
-  int na = (q->KH * q->KW == 1) ? 4 : 2;
+  int na = (q->KH * q->KW == 1 && !p->kgroup) ? 4 : 2;
   if (na > nblk) na = nblk;
   if (na * a_slot + b_slot > CV_SMEM_BUDGET) na = 1;
   if (na * a_slot + b_slot > CV_SMEM_BUDGET) return PP_ERR_SHAPE;
@@ -421,7 +437,7 @@ extern "C" int pp_conv2d_umma(const PPConvParams* q, cudaStream_t stream) {
       return PP_ERR_LAUNCH;
   }
   {
-    const cuuint64_t ktot = (cuuint64_t)p.nblk * p.KH * p.KW * 32;
+    const cuuint64_t ktot = (cuuint64_t)p.kreal * q->KH * q->KW * 32;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)q->Cout};
     cuuint64_t strides[1] = {ktot * 4};
     cuuint32_t box[2] = {32, (cuuint32_t)p.BN};

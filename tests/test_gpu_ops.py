@@ -197,6 +197,7 @@ def test_conv_umma_matches_torch_conv():
         (1, 30, 54, [2304], 128, 1, 1, "none", False, False, False, 0, 0),        # deformable-conv GEMM over sampled columns
         (2, 30, 54, [256], 128, 1, 5, "tanh", False, False, False, 0, 0),         # SepConvGRU shapes
         (2, 30, 54, [256], 128, 5, 1, "none", False, False, False, 0, 0),
+        (1, 30, 54, [160, 96], 128, 1, 1, "none", False, True, False, 0, 0),       # 1x1, grouped k-blocks, ragged segment ends
         (1, 30, 54, [128, 128], 128, 3, 3, "leaky", True, True, False, 64, -8),   # M = 64 tiles (8x8 pixels)
         (2, 33, 21, [128], 432, 3, 3, "none", False, False, False, 128, -16),     # M = 64 tiles (4x16 pixels), ragged map
     ]
