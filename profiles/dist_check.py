@@ -18,8 +18,13 @@ T, sub = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (33, 10)
 u8, fm, md = synth.make_clip(T, 240, 432, mask="ellipse", seed=0)
 pipe = ProPainterPipeline(device=f"cuda:{local}")
 cfg = InferenceConfig(raft_iter=4, subvideo_length=sub)
-a = ShardedProPainter(pipe)(torch.from_numpy(u8), fm, md, cfg)
+sp = ShardedProPainter(pipe)
+a = sp(torch.from_numpy(u8), fm, md, cfg, gather=True)
+part, ids = sp(torch.from_numpy(u8), fm, md, cfg)                # the product path: every rank keeps its own final frames
 torch.cuda.synchronize()
+assert torch.equal(part, a[ids])
+print(f"rank {dist.get_rank()}: holds {len(ids)} final frames, sent {sum(sp.last_bytes.values()) / 1e6:.1f} MB point to point: "
+      + ", ".join(f"{k} {v / 1e6:.1f}" for k, v in sp.last_bytes.items()), flush=True)
 if dist.get_rank() == 0:
     b = pipe(torch.from_numpy(u8), fm, md, cfg)
     d = np.abs(a.cpu().numpy().astype(int) - b.cpu().numpy().astype(int))
