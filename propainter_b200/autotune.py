@@ -11,13 +11,17 @@ import torch
 from . import config
 
 _choice = {}
+_timings = {}          # (key, variant) -> ms per run of the graph-timed candidates (reported by bench.py)
 
 
 def choices():
     return dict(_choice)
 
 
-def pick(key, variants, *args, reps=5):
+def pick(key, variants, *args, reps=5, graph_timed=False):
+    """graph_timed: time every candidate as a captured CUDA graph (device time of the launch sequence, the way the stage
+    will actually run) instead of eagerly -- for plans made of many small kernels an eager timing measures the host's
+    launch rate, not the GPU."""
     i = _choice.get(key)
     if i is None:
         if not config.AUTOTUNE or not args[0].is_cuda or torch.cuda.is_current_stream_capturing():
@@ -27,15 +31,25 @@ def pick(key, variants, *args, reps=5):
             try:
                 fn(*args)
                 fn(*args)                                   # cuDNN algorithm search / lazy packing happen here
+                run = lambda: fn(*args)
+                if graph_timed:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn(*args)
+                    run = g.replay
+                    run()
             except RuntimeError:
                 continue                                    # plan not supported for this shape by the library
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                fn(*args)
+                run()
             e1.record()
             e1.synchronize()
             t = e0.elapsed_time(e1)
+            if graph_timed:
+                _timings[(key, j)] = t / reps
             if best is None or t < best:
                 best, i = t, j
         _choice[key] = i

@@ -10,7 +10,9 @@ CUDA_GRAPHS     replay each stage as a captured CUDA graph per shape signature (
 FUSED_EPILOGUE  conv bias + activation through pp_bias_act (one pass) instead of cuDNN's bias add_ + ATen activation.
 UMMA_CONV       the convolutions of the two recurrent propagation scans (offset nets, backbones, deformable-conv GEMM) run on
                 the tcgen05 implicit-GEMM kernel pp_conv2d_umma (TF32 products, fused bias / activation / residual / concat
-                epilogue) instead of cuDNN + pp_bias_act + the mma.sync deform kernel.
+                epilogue) instead of cuDNN + pp_bias_act + the mma.sync deform kernel.  True / False force one plan;
+                "auto" (default) times both plans of a scan once per shape during graph warm-up (autotune.pick) and replays
+                the faster one.  Environment: PP_UMMA_CONV=1|0|auto.
 AUTOTUNE        time numerically equivalent plans of a step once per shape during warm-up and keep the faster
                 (propainter_b200/autotune.py): grouped conv vs per-group dense convs, conv + pp_bias_act vs cuDNN's fused
                 conv-bias-ReLU.
@@ -25,7 +27,8 @@ CUDNN_BENCHMARK = True
 CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
-UMMA_CONV = os.environ.get("PP_UMMA_CONV", "1") != "0"      # PP_UMMA_CONV=0: library convs + mma.sync deform kernel
+_u = os.environ.get("PP_UMMA_CONV", "auto")
+UMMA_CONV = "auto" if _u == "auto" else (_u != "0")
 
 
 @contextlib.contextmanager

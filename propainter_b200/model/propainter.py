@@ -299,12 +299,17 @@ class InpaintGenerator(ParamNet):
         H2, W2 = padded_grid(fh, fw, WIN)
         flags = ops.window_mask(pmask, fh, fw, H2 // WIN[0], W2 // WIN[1])
         enc_pm = as_pm(enc)
-        if config.UMMA_CONV:
-            if interpolation != "bilinear":
-                raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
-            local = self._feat_propagation_umma(enc_pm[:lt], dsf, dsb, pmask)
+        if interpolation != "bilinear":
+            raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
+        xl = enc_pm[:lt]
+        if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
+            local = autotune.pick(("gen_prop", tuple(xl.shape)), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
+                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation)),
+                                  xl, dsf, dsb, pmask, reps=2, graph_timed=True)
+        elif config.UMMA_CONV:
+            local = self._feat_propagation_umma(xl, dsf, dsb, pmask)
         else:
-            local = self._feat_propagation(enc_pm[:lt], dsf, dsb, pmask, interpolation)
+            local = self._feat_propagation(xl, dsf, dsb, pmask, interpolation)
         enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
         tok_in = self.tx.soft_split(enc2)
         tok = self.tx.run(tok_in, (h, w), flags, t_dilation)

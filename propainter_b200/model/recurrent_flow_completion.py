@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import config, ops
+from .. import autotune, config, ops
 from .._params import ParamNet
 from ..nn_util import as_nchw, as_pm, cl, conv, up2
 from ..schemas import rfc_schema
@@ -192,7 +192,10 @@ class RecurrentFlowCompleteNet(ParamNet):
         m = e2
         for i, d in ((0, 3), (2, 2), (4, 1)):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
-        fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
+        if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
+            fpr = autotune.pick(("rfc_prop", tuple(m.shape)), (self._propagate_umma, self._propagate), m, reps=2, graph_timed=True)
+        else:
+            fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
         d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
         d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
         fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
