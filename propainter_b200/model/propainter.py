@@ -303,7 +303,7 @@ class InpaintGenerator(ParamNet):
             raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
         xl = enc_pm[:lt]
         if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
-            local = autotune.pick(("gen_prop", tuple(xl.shape)), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
+            local = autotune.pick(("gen_prop", tuple(xl.shape[1:])), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
                                                                   lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation)),
                                   xl, dsf, dsb, pmask, reps=2, graph_timed=True)
         elif config.UMMA_CONV:

@@ -193,7 +193,7 @@ class RecurrentFlowCompleteNet(ParamNet):
         for i, d in ((0, 3), (2, 2), (4, 1)):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
         if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
-            fpr = autotune.pick(("rfc_prop", tuple(m.shape)), (self._propagate_umma, self._propagate), m, reps=2, graph_timed=True)
+            fpr = autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate), m, reps=2, graph_timed=True)
         else:
             fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
         d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
