@@ -223,12 +223,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     const float slope = p.slope;
     // M = 128: warp w's 32 TMEM lanes hold accumulator rows 32w .. 32w+31; M = 64: rows 16w .. 16w+15 in lanes 0-15 (the
     // "half subpartition" layout of cta_group::1 M=64 accumulators, cute/atom/mma_traits_sm100.hpp), lanes 16-31 unused
-    const int rpw = p.M >> 2;
+    const int rpw = p.M >> 2, bw_shift = p.BW == 16 ? 4 : 3;
     long pixi[8];                                                   // pixel index of row 4i + rsub of this warp's rows (-1: none / outside the map)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = 4 * i + rsub, r = warp * rpw + rl;
-      const int y = y0 + r / p.BW, x = x0 + r % p.BW;
+      const int y = y0 + (r >> bw_shift), x = x0 + (r & (p.BW - 1));      // BW is 8 or 16: no runtime division (ptxas sank the
+                                                                       // div/mod sequences into the store loop: 2.4 k cycles)
       pixi[i] = (rl < rpw && y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
     }
     const int nchunk = p.BN >> 5;

@@ -236,7 +236,7 @@ def test_conv_umma_matches_torch_conv():
     y = ops.conv_umma([x], ops.pack_conv_weight(w).to(DEV), 3, 3, 32, round_tf32=True)
     assert torch.equal(y, ops.tf32_round(y))
     with pytest.raises(RuntimeError):
-        ops.conv_umma([x[..., :30]], ops.pack_conv_weight(w).to(DEV), 3, 3, 32)                # packed weight / segment mismatch
+        ops.conv_umma([x], ops.pack_conv_weight(torch.randn(32, 64, 3, 3)).to(DEV), 3, 3, 32)   # packed weight / segment mismatch
 
 
 def test_deform_gather_plus_gemm():
