@@ -222,16 +222,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
     const int act = p.act, post_relu = p.post_relu, round_tf32 = p.round_tf32;
     const float slope = p.slope;
     // M = 128: warp w's 32 TMEM lanes hold accumulator rows 32w .. 32w+31; M = 64: rows 16w .. 16w+15 in lanes 0-15 (the
-    // "half subpartition" layout of cta_group::1 M=64 accumulators, cute/atom/mma_traits_sm100.hpp), lanes 16-31 unused
+    // "half subpartition" layout of cta_group::1 M=64 accumulators, cute/atom/mma_traits_sm100.hpp), lanes 16-31 unused.
+    // The row pointers of this lane's 8 rows (row = 4i + lane/8) are built here, while the MMAs still run: the epilogue is
+    // one warp per scheduler, so every instruction of its dependent address arithmetic costs ~4 cycles of latency, and
+    // computing them per 32-column chunk (~1000 instructions with the 64-bit index math) was 2.4 k cycles per chunk.
     const int rpw = p.M >> 2, bw_shift = p.BW == 16 ? 4 : 3;
-    long pixi[8];                                                   // pixel index of row 4i + rsub of this warp's rows (-1: none / outside the map)
+    const float* prow[8]; const float* rrow[8]; float* orow[8];
+    unsigned okmask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = 4 * i + rsub, r = warp * rpw + rl;
-      const int y = y0 + (r >> bw_shift), x = x0 + (r & (p.BW - 1));      // BW is 8 or 16: no runtime division (ptxas sank the
-                                                                       // div/mod sequences into the store loop: 2.4 k cycles)
-      pixi[i] = (rl < rpw && y < p.H && x < p.W) ? ((long)img * p.H + y) * p.W + x : -1;
+      const int y = y0 + (r >> bw_shift), x = x0 + (r & (p.BW - 1));
+      const bool ok = rl < rpw && y < p.H && x < p.W;
+      const long pix = ok ? ((long)img * p.H + y) * p.W + x : 0;
+      okmask |= ok ? (1u << i) : 0u;
+      orow[i] = p.out + pix * p.ld_out + n0 + 4 * c4;
+      prow[i] = p.pre ? p.pre + pix * p.ld_pre + n0 + 4 * c4 : nullptr;
+      rrow[i] = p.res ? p.res + pix * p.ld_res + n0 + 4 * c4 : nullptr;
+      asm volatile("" : "+l"(orow[i]), "+l"(prow[i]), "+l"(rrow[i]));        // keep them materialised here (no sinking into the loop)
     }
+    const bool has_pre = p.pre != nullptr, has_res = p.res != nullptr;
     const int nchunk = p.BN >> 5;
     float* stgw = reinterpret_cast<float*>(sA) + warp * nchunk * (32 * 36);      // this warp's staging tiles, one per 32 columns
     ua_bar_wait(bar(32), 0);
@@ -259,11 +269,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
       const float* stg = stgw + ch * (32 * 36);
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), pv[8], rv[8];
       if (bias && n_in) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+      const unsigned on = n_in ? okmask : 0u;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const bool on = n_in && pixi[i] >= 0;
-        pv[i] = (p.pre && on) ? *reinterpret_cast<const float4*>(p.pre + pixi[i] * p.ld_pre + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rv[i] = (p.res && on) ? *reinterpret_cast<const float4*>(p.res + pixi[i] * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[i] = (has_pre && ((on >> i) & 1)) ? *reinterpret_cast<const float4*>(prow[i] + ch * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rv[i] = (has_res && ((on >> i) & 1)) ? *reinterpret_cast<const float4*>(rrow[i] + ch * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // the activation is selected once per chunk (warp-uniform branch), not per element: with the switch inside the
       // element loop ptxas inlined the exp / tanh paths 32 times per chunk (~260 instructions between each shared-memory
@@ -274,7 +284,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
       auto finish = [&](auto actf) {
         float4 a[8];
 #pragma unroll
+#ifdef CV_DBG_NOLDS
+        for (int i = 0; i < 8; ++i) a[i] = make_float4(1.f, 2.f, 3.f, (float)i);
+#else
         for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
+#endif
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           a[i].x = actf(a[i].x + (bv.x + pv[i].x)) + rv[i].x; a[i].y = actf(a[i].y + (bv.y + pv[i].y)) + rv[i].y;
@@ -287,7 +301,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (n_in && pixi[i] >= 0) *reinterpret_cast<float4*>(p.out + pixi[i] * p.ld_out + n) = a[i];
+#ifdef CV_DBG_NOSTG
+          if (((on >> i) & 1) && a[i].x == 12345.678f) *reinterpret_cast<float4*>(orow[i] + ch * 32) = a[i];
+#else
+          if ((on >> i) & 1) *reinterpret_cast<float4*>(orow[i] + ch * 32) = a[i];
+#endif
       };
       if (act == 0) finish([](float v) { return v; });
       else if (act == 1) finish([](float v) { return fmaxf(v, 0.f); });
