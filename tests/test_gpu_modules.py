@@ -55,7 +55,7 @@ def test_raft_bi_matches_oracle():
         e1, e2 = rel_err(fw.cpu(), rf), rel_err(bw.cpu(), rb)
         epe = ((fw.cpu() - rf) ** 2).sum(2).sqrt().mean().item()
         print(f"raft iters={iters}: rel {e1:.2e} {e2:.2e}  EPE {epe:.4f}px  |flow|max {rf.abs().max():.2f}")
-        assert e1 < 2e-3 and e2 < 2e-3 and epe < 0.05
+        assert e1 < 1e-4 and e2 < 1e-4 and epe < 0.01          # measured 3.6e-6 (fp32 library convs in this test)
     # generic two-image entry point (reference RAFT.forward signature)
     lo, up = net.fix_raft(frames[0, :2].to(DEV), frames[0, 1:3].to(DEV), iters=2, test_mode=True)
     rlo, rup = raft_ref.raft_forward(cpu_sd(net.fix_raft), frames[0, :2], frames[0, 1:3], 2, return_lowres=True)
@@ -75,7 +75,7 @@ def test_flow_completion_matches_oracle():
     for a, b in zip(pred, ref):
         e = rel_err(a.cpu(), b)
         print(f"rfc rel {e:.2e} scale {b.abs().max():.3f}")
-        assert e < 1e-2
+        assert e < 2e-3                                          # measured 1.5e-4 (TF32 deform GEMM / scan convs)
     assert edges == [None, None]
     comb = net.combine_flow((flows[0].to(DEV), flows[1].to(DEV)), pred, masks.to(DEV))
     rc = flowcomp_ref.combine_flow(flows, ref, masks)
@@ -176,7 +176,7 @@ def test_pipeline_c1_matches_oracle():
     psnr = ops_ref.psnr_u8(comp, ref)
     inside = md[0, :, 0].bool().numpy()
     print(f"updated-mask mismatch {mm:.2e}; final PSNR {psnr:.2f} dB; max diff {np.abs(comp.astype(int) - ref.astype(int)).max()}")
-    assert mm < 5e-3 and psnr > 40.0
+    assert mm < 5e-3 and psnr > 60.0                              # measured 71 dB, max diff 1 level
     assert np.array_equal(comp[~inside], ref[~inside])            # outside the mask the original pixels are kept
 
 
@@ -185,7 +185,7 @@ def test_pipeline_chunked_long_clip():
     comp, st, ref, rst, md = _run_both(23, 128, 128, "ellipse", 2, sub=10)
     psnr = ops_ref.psnr_u8(comp, ref)
     print(f"chunked: PSNR {psnr:.2f} dB")
-    assert psnr > 38.0
+    assert psnr > 60.0                                            # measured 76 dB
 
 
 @pytest.mark.shipping
@@ -203,7 +203,7 @@ def test_pipeline_shipping_defaults_vs_golden_and_oracle():
     assert np.array_equal(a, b)
     psnr = ops_ref.psnr_u8(a, g["comp"])
     print(f"shipping defaults vs reference golden: PSNR {psnr:.2f} dB, max diff {np.abs(a.astype(int) - g['comp'].astype(int)).max()}")
-    assert psnr > 40.0
+    assert psnr > 58.0                                            # measured 68.6 dB, max diff 1 level
 
 
 def test_weight_reload_drops_captured_graphs():
@@ -240,7 +240,7 @@ def test_pipeline_720p_and_border_mask():
         ref = pipeline_ref.run_pipeline(sds, u8, fm, md, raft_iter=2)
         psnr = ops_ref.psnr_u8(comp, ref)
         print(f"{W}x{H} T={T} mask={mask}: PSNR {psnr:.2f} dB vs oracle")
-        assert psnr > 40.0
+        assert psnr > 58.0                                        # measured 71.8 / 67.1 dB
 
 
 

@@ -62,9 +62,11 @@ def test_full_size_vs_reference_golden(key):
     print(f"{key}: " + " ".join(f"{k}={v:.2e}" for k, v in e.items()) +
           f" | PSNR {psnr:.2f} dB (holes only {psnr_hole:.2f} dB), max |diff| {d.max()}, >1 level: {(d > 1).mean():.2e}")
     assert np.array_equal(a[~hole], u8[~hole])
-    assert e["gt_f"] < 2e-2 and e["gt_b"] < 2e-2 and e["pred_f"] < 5e-2 and e["pred_b"] < 5e-2
-    assert e["upd_m_mismatch"] < 5e-3 and e["upd_f_mismatch"] < 2e-2
-    assert psnr_hole > 40.0 and psnr > 45.0
+    # measured on B200 (round 2): flows 1.4e-3 / 1.5e-3 (TF32 library convs in RAFT), masks and propagated frames exact,
+    # PSNR 72.1 dB (C2) / 67.2 dB (C3), 61.1 dB inside the holes, max |diff| 1 level
+    assert e["gt_f"] < 1e-2 and e["gt_b"] < 1e-2 and e["pred_f"] < 1e-2 and e["pred_b"] < 1e-2
+    assert e["upd_m_mismatch"] < 1e-3 and e["upd_f_mismatch"] < 1e-3
+    assert psnr_hole > 52.0 and psnr > 60.0 and d.max() <= 4
 
 
 def test_oracle_pinned_at_full_size():
