@@ -257,7 +257,7 @@ def roofline_probe(torch, pipe, wl):
     ms = _time_kernel(torch, lambda: ops.sparse_window_attn(qkv, pool, ktab, flags, t, H2 * W2, 0, 2))
     ach = flops / (ms * 1e-3) / 1e12
     primary = {"kernel": "k_sparse_attn_umma (+ unmasked-window kernel)", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": 29.65e6, "peak_source": src + " bf16_tflops / 2 (TF32)",
+               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None, "peak_source": src + " bf16_tflops / 2 (TF32)",
                "launch_ms": ms, "algorithmic_flops": flops, "masked_windows": f"{nmask} of {nwin}"}
     # ---- RAFT correlation lookup, one refinement step of the whole clip
     h, w = wl["H"] // 8, wl["W"] // 8
@@ -273,19 +273,32 @@ def roofline_probe(torch, pipe, wl):
     npx = h * w
     alg = B * (npx * 4 * 100 * 4 + npx * 324 * 4 + npx * 8)        # unique 10x10 patches at 4 levels + 324-ch output + coords
     ach_l = alg / (ms_l * 1e-3) / 1e9
-    # ---- deformable alignment, one generator propagation step
+    # ---- deformable alignment, one generator propagation step: sampling kernel + tcgen05 GEMM over the sampled columns
     Hh, Ww = wl["H"] // 4, wl["W"] // 4
-    x, o = torch.randn(Hh, Ww, 128, device=dev), torch.randn(Hh, Ww, 432, device=dev)
-    fl, wp = torch.randn(Hh, Ww, 2, device=dev), torch.randn(9 * 128, 128, device=dev) * 0.03
-    bvec, dout = torch.randn(128, device=dev), torch.empty(Hh, Ww, 128, device=dev)
-    ms_d = _time_kernel(torch, lambda: ops.deform_align(x, o, fl, 3.0, wp, bvec, dout))
+    x, o = torch.randn(1, Hh, Ww, 128, device=dev), torch.randn(1, Hh, Ww, 432, device=dev)
+    fl = torch.randn(1, Hh, Ww, 2, device=dev)
+    wd = ops.pack_deform_weight_umma(torch.randn(128, 128, 3, 3, device=dev) * 0.03)
+    bvec, dout = torch.randn(128, device=dev), torch.empty(1, Hh, Ww, 128, device=dev)
+    cols = torch.empty(1, Hh, Ww, 9 * 128, device=dev)
+    ms_g = _time_kernel(torch, lambda: ops.deform_gather(x, o, fl, 3.0, cols))
+    ms_m = _time_kernel(torch, lambda: ops.conv_umma([cols], wd, 1, 1, 128, bias=bvec, out=dout))
     fl_d = Hh * Ww * 9 * 128 * 128 * 2
+    # ---- the tcgen05 conv kernel on one 3x3 128->128 conv of a generator propagation step (bias + LeakyReLU + residual fused)
+    xc = torch.randn(1, Hh, Ww, 128, device=dev)
+    wc = ops.pack_conv_weight(torch.randn(128, 128, 3, 3, device=dev) * 0.03)
+    rc, oc = torch.randn(1, Hh, Ww, 128, device=dev), torch.empty(1, Hh, Ww, 128, device=dev)
+    ms_c = _time_kernel(torch, lambda: ops.conv_umma([xc], wc, 3, 3, 128, bias=bvec, act="leaky", slope=0.1, res=rc, out=oc))
+    fl_c = Hh * Ww * 9 * 128 * 128 * 2
     primary["others"] = [
         {"key": "corr_lookup", "kernel": "k_corr_lookup_tma", "bound": "hbm", "achieved": ach_l, "peak": hbm, "unit": "GB/s", "frac": ach_l / hbm,
-         "traffic": 124.8e6 * B / 22, "launch_ms": ms_l, "algorithmic_bytes": alg},
-        {"key": "deform", "kernel": "k_deform_align (+ split-K reduce)", "bound": "tensor", "achieved": fl_d / (ms_d * 1e-3) / 1e12, "peak": tf32_peak,
-         "unit": "TFLOP/s", "frac": fl_d / (ms_d * 1e-3) / 1e12 / tf32_peak, "traffic": 36.7e6, "launch_ms": ms_d,
-         "algorithmic_flops": fl_d, "note": "warp-level mma.sync TF32 (legacy tensor path), latency-bound gather"}]
+         "traffic": None, "launch_ms": ms_l, "algorithmic_bytes": alg},
+        {"key": "deform", "kernel": "k_deform_gather + k_conv_umma (1x1 over the sampled columns)", "bound": "tensor",
+         "achieved": fl_d / ((ms_g + ms_m) * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+         "frac": fl_d / ((ms_g + ms_m) * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_g + ms_m, "gather_ms": ms_g, "gemm_ms": ms_m,
+         "algorithmic_flops": fl_d, "note": "two launches; the gather is L2-bandwidth bound (119 MB of corner reads per step)"},
+        {"key": "conv", "kernel": "k_conv_umma 3x3 128->128 on the 60x108 map", "bound": "tensor", "achieved": fl_c / (ms_c * 1e-3) / 1e12,
+         "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl_c / (ms_c * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_c,
+         "algorithmic_flops": fl_c, "note": "single launch incl. launch latency; 112 CTAs on 148 SMs; tf32 operands from shared memory"}]
     return primary
 
 

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-PROF_QUICK=1 PROPAINTER_B200_LIB=$PWD/propainter_b200/libpropainter_b200_prof.so timeout 100 python profiles/conv_prof.py 2>&1 | tail -4
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_modules.py -q -m gpu -s > gpurun_out/pytest_om8.log 2>&1; grep -v "^$" gpurun_out/pytest_om8.log | tail -25
-timeout 900 python -m pytest tests/test_gpu_zz_full_size.py -q -m gpu -s > gpurun_out/pytest_full8.log 2>&1; grep -v "^$" gpurun_out/pytest_full8.log | tail -12
+timeout 900 python bench.py --steps 5 --warmup 3 --no-strong > gpurun_out/bench_c.log 2> gpurun_out/bench_c.err; tail -c 3000 gpurun_out/bench_c.log; tail -3 gpurun_out/bench_c.err | cut -c1-300
+timeout 600 python bench.py --steps 6 --warmup 3 --no-strong --no-gpu-reference --no-cpu-baseline --clips-in-flight 2 > gpurun_out/bench_d.log 2> gpurun_out/bench_d.err; tail -c 1500 gpurun_out/bench_d.log; tail -3 gpurun_out/bench_d.err | cut -c1-300
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; tail -c 1200 gpurun_out/bench_ref.log
