@@ -1,6 +1,6 @@
 // RAFT correlation lookup, TMA-staged (sm_100a).
 //
-// A warp per source pixel at a time (persistent warps, two-stage ring).  For each of the 4 pyramid levels lane 0 issues one
+// One warp per source pixel.  For each of the 4 pyramid levels the warp's elected lane issues one
 // cp.async.bulk.tensor (TMA, 3-D tiled: x, y, plane) that lands the 16x10 neighbourhood of the lookup
 // centre in shared memory (the box's innermost coordinate is rounded down to a multiple of 4 floats: a
 // tiled TMA load whose first element is not 16-byte aligned faults with "illegal instruction" -- measured
@@ -12,12 +12,11 @@
 #include "pp_elem.cuh"
 #include "../../include/propainter_b200.h"
 
-#define LK_WARPS 4
-#define LK_STAGES 2
+#define LK_WARPS 8
 #define LK_BOX 10                       // rows of the staged box: taps b = 0..8 read rows b and b+1
 #define LK_BOXW 16                      // columns: 10 needed + up to 3 because the box must start 16-byte aligned
 #define LK_HALF 4
-#define LK_LVL_FLOATS 192               // 640 B box + pad: level l's box starts 768 B after level l-1's
+#define LK_LVL_FLOATS 192               // 640 B box + pad: level l's box starts 768 B (+0 banks) after level l-1's
 
 __device__ __forceinline__ uint32_t lk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -27,89 +26,69 @@ __device__ __forceinline__ int lk_base(float c, float inv) {
   return (int)v - LK_HALF;
 }
 
-// Persistent warps with a two-stage ring: warp w looks up pixels w, w + W, w + 2W, ... and issues the four TMA boxes of its
-// next pixel before it blends the current one, so every warp always has 2.5 KB of loads in flight while it computes and
-// stores (round 1: one pixel per warp, load -> wait -> blend -> store strictly in sequence; 46 % of HBM peak at 158 pairs).
 __global__ void __launch_bounds__(LK_WARPS * 32) k_corr_lookup_tma(const __grid_constant__ CUtensorMap tm0,
     const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
     const __grid_constant__ CUtensorMap tm3, const float* __restrict__ coords, float* __restrict__ out, long npix,
     int h, int w) {
-  __shared__ __align__(128) float patch[LK_WARPS][LK_STAGES][4][LK_LVL_FLOATS];
-  __shared__ __align__(8) unsigned long long bar[LK_WARPS][LK_STAGES];
+  __shared__ __align__(128) float patch[LK_WARPS][4][LK_LVL_FLOATS];
+  __shared__ __align__(8) unsigned long long bar[LK_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long gw = (long)blockIdx.x * LK_WARPS + warp, nw = (long)gridDim.x * LK_WARPS;
-  if (gw >= npix) return;
-  const long n_my = (npix - gw + nw - 1) / nw;
-  if (lane == 0) {
+  const long pix = (long)blockIdx.x * LK_WARPS + warp;
+  if (pix >= npix) return;
+  const float cx = coords[2 * pix], cy = coords[2 * pix + 1];
+  const uint32_t bar_a = lk_smem(&bar[warp]);
+  int bx[4], by[4];
 #pragma unroll
-    for (int s = 0; s < LK_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem(&bar[warp][s])));
+  for (int l = 0; l < 4; ++l) { bx[l] = lk_base(cx, 1.0f / (float)(1 << l)) & ~3; by[l] = lk_base(cy, 1.0f / (float)(1 << l)); }
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  auto issue = [&](long i) {                                        // lane 0: the four boxes of this warp's i-th pixel
-    const int s = (int)(i & 1);
-    const long pix = gw + i * nw;
-    const float cx = coords[2 * pix], cy = coords[2 * pix + 1];
-    const uint32_t bar_a = lk_smem(&bar[warp][s]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(4 * LK_BOX * LK_BOXW * 4) : "memory");
     const CUtensorMap* tms[4] = {&tm0, &tm1, &tm2, &tm3};
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const float inv = 1.0f / (float)(1 << l);
+    for (int l = 0; l < 4; ++l)
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(lk_smem(&patch[warp][s][l][0])), "l"(tms[l]), "r"(lk_base(cx, inv) & ~3), "r"(lk_base(cy, inv)), "r"((int)pix), "r"(bar_a)
-          : "memory");
-    }
-  };
-  if (lane == 0) issue(0);
-  for (long i = 0; i < n_my; ++i) {
-    const int s = (int)(i & 1);
-    if (lane == 0 && i + 1 < n_my) issue(i + 1);                    // stage (i+1)&1 was released by the __syncwarp closing iteration i-1
-    const long pix = gw + i * nw;
-    const float cx = coords[2 * pix], cy = coords[2 * pix + 1];
-    {                                     // wait for the 4 boxes, bounded spin
-      const uint32_t bar_a = lk_smem(&bar[warp][s]), parity = (uint32_t)((i >> 1) & 1);
-      uint32_t done = 0;
-      for (int spin = 0; spin < (1 << 22) && !done; ++spin)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
-      if (!done) __trap();
-    }
-    float* o = out + pix * 324;
-    // Two passes of two levels; 9 lanes per level (lane <-> x-tap a) slide down the 10 staged rows, so each shared-memory
-    // value is read once per column pair and the 9 results of a lane are 9 consecutive output floats (index l*81 + a*9 + b).
-    // The second level of a pass runs one row behind the first: at every step the two groups read rows of opposite parity,
-    // i.e. opposite halves of the 32 banks (rows are 16 floats) -- no bank conflicts between levels (round 1: 2.2-way).
-    // All taps of a level share the fractional part of the centre (integer tap offsets): corners outside the image read
-    // the zeros TMA filled in.  (The reference sends every tap through grid_sample's normalise / un-normalise round trip,
-    // RAFT/utils/utils.py:60-65, which only adds ~1e-6 px of rounding noise -- dropped, well inside the 1e-4 tolerance.)
-    const int grp = lane / 9, a = lane - 9 * grp;
-    const bool act = lane < 18;
+          ::"r"(lk_smem(&patch[warp][l][0])), "l"(tms[l]), "r"(bx[l]), "r"(by[l]), "r"((int)pix), "r"(bar_a) : "memory");
+  }
+  __syncwarp();
+  {                                       // wait for the 4 boxes (phase 0), bounded spin
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar_a) : "memory");
+    if (!done) __trap();
+  }
+  float* o = out + pix * 324;
+  // Register-blocked along y: a lane owns one (level, x-tap a) column and slides down the 10 staged rows, so each
+  // shared-memory value is read once per column pair (20 loads for 9 taps instead of 36) and the 9 results of a lane
+  // are 9 consecutive output floats (index l*81 + a*9 + b).  Pass 0: levels 0-2 (27 lanes), pass 1: level 3 (9 lanes).
+  // All taps of a level share the fractional part of the centre (integer tap offsets): corners outside the image read
+  // the zeros TMA filled in.  (The reference sends every tap through grid_sample's normalise / un-normalise round trip,
+  // RAFT/utils/utils.py:60-65, which only adds ~1e-6 px of rounding noise -- dropped, well inside the 1e-4 tolerance.)
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int l = 2 * pass + grp;
-      const float inv = 1.0f / (float)(1 << (l & 3));
+  for (int pass = 0; pass < 2; ++pass) {
+    const int l = pass == 0 ? lane / 9 : 3, a = pass == 0 ? lane - 9 * (lane / 9) : lane;
+    const bool act = pass == 0 ? lane < 27 : lane < 9;
+    if (act) {
+      const float inv = 1.0f / (float)(1 << l);
       const float xl = cx * inv, yl = cy * inv;
       const bool sane = fabsf(xl) < 1.0e6f && fabsf(yl) < 1.0e6f;
       const float wx1 = sane ? xl - floorf(xl) : 0.f, wy1 = sane ? yl - floorf(yl) : 0.f;
       const float wx0 = sane ? 1.0f - wx1 : 0.f, wy0 = sane ? 1.0f - wy1 : 0.f;
-      const int b0 = lk_base(cx, inv);
-      const float* q = &patch[warp][s][l & 3][0] + (b0 - (b0 & ~3)) + a;          // row 0 of this lane's column pair
-      float top = act ? wx0 * q[0] + wx1 * q[1] : 0.f;
-      float* ol = o + (l & 3) * 81 + a * 9;
+      int bxl = bx[0];
+      if (l == 1) bxl = bx[1]; else if (l == 2) bxl = bx[2]; else if (l == 3) bxl = bx[3];
+      const float* q = &patch[warp][l][0] + (lk_base(cx, inv) - bxl) + a;      // row 0 of this lane's column pair
+      float top = wx0 * q[0] + wx1 * q[1];
+      float* ol = o + l * 81 + a * 9;
 #pragma unroll
-      for (int step = 0; step < 10; ++step) {
-        const int b = step - grp;                                                 // group 1 lags one row
-        if (act && b >= 0 && b < 9) {
-          const float* r = q + (b + 1) * LK_BOXW;
-          const float bot = wx0 * r[0] + wx1 * r[1];
-          ol[b] = wy0 * top + wy1 * bot;
-          top = bot;
-        }
+      for (int b = 0; b < 9; ++b) {
+        q += LK_BOXW;
+        const float bot = wx0 * q[0] + wx1 * q[1];
+        ol[b] = wy0 * top + wy1 * bot;
+        top = bot;
       }
     }
-    __syncwarp();                                                   // every lane is done with stage s before it is refilled
   }
 }
 
@@ -148,10 +127,8 @@ extern "C" int pp_corr_lookup(const float* const* levels, const float* coords, f
     if (r != CUDA_SUCCESS) return PP_ERR_LAUNCH;
     hl >>= 1; wl >>= 1;
   }
-  // persistent grid: 9 blocks of 4 warps per SM (24.6 KB of staging each), warps stride over the pixels
-  long blocks = (npix + LK_WARPS - 1) / LK_WARPS;
-  if (blocks > 9L * PP_NUM_SMS) blocks = 9L * PP_NUM_SMS;
-  k_corr_lookup_tma<<<(int)blocks, LK_WARPS * 32, 0, stream>>>(tm[0], tm[1], tm[2], tm[3], coords, out, npix, h, w);
+  k_corr_lookup_tma<<<(int)((npix + LK_WARPS - 1) / LK_WARPS), LK_WARPS * 32, 0, stream>>>(tm[0], tm[1], tm[2], tm[3],
+                                                                                           coords, out, npix, h, w);
   if (cudaPeekAtLastError() != cudaSuccess) return PP_ERR_LAUNCH;
   return PP_OK;
 }
