@@ -85,9 +85,36 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
+def _usable_cores():
+    """Physical cores this process may use: min(affinity mask, cgroup CPU quota, physical cores in /proc/cpuinfo).
+    One thread per hyper-thread sibling made the oracle 19x slower than one per core on the GPU box (128 vs 64 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    try:
+        cores, phys, core = set(), None, None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip() and phys is not None and core is not None:
+                cores.add((phys, core))
+                phys = core = None
+        if cores:
+            n = min(n, len(cores))
+    except OSError:
+        pass
+    return max(1, n)
+
+
 def _host_threads(torch):
-    """Use every host core for the CPU arm whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
-    n = os.cpu_count() or 1
+    """Every usable physical core for the CPU arm whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    n = _usable_cores()
     torch.set_num_threads(n)
     return n
 

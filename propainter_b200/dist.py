@@ -244,7 +244,7 @@ class ShardedProPainter:
         enc = {}
         if own:
             u = self._stack(upd, own)
-            e_own = pipe.model.encode(u[:, :3], md_all[own], u[:, 3:4]).permute(0, 2, 3, 1)   # pixel-major [n,h,w,128]
+            e_own = pipe.model.encode(u[:, :3], md_all[own[0]:own[-1] + 1], u[:, 3:4]).permute(0, 2, 3, 1)   # pixel-major [n,h,w,128]; own is a contiguous range
             for j, i in enumerate(own):
                 enc[i] = e_own[j]
             eshape = tuple(e_own.shape[1:])
@@ -271,7 +271,7 @@ class ShardedProPainter:
             return lambda slot: pipe.model.forward_features(
                 self._stack(enc, ids).permute(0, 3, 1, 2),
                 (self._stack(pred[0], nb[:-1]) if len(nb) > 1 else empty, self._stack(pred[1], nb[:-1]) if len(nb) > 1 else empty),
-                md_all[ids], self._stack(um1, ids), len(nb), slot=slot)
+                md_all.index_select(0, pipe.index(ids)), self._stack(um1, ids), len(nb), slot=slot)
         # the window predictions do not depend on the seam: compute them all (several in flight), composite afterwards in order
         pipe.run_windows([job(wi) for wi in mine_w], lambda k, p: preds.__setitem__(mine_w[k], p), cfg, ori.is_cuda)
         earlier = {f for wi in range(len(plan)) if owner[wi] < rank for f in plan[wi][0]}
@@ -280,12 +280,12 @@ class ShardedProPainter:
         if need and prev is not None:
             buf = comp.new_empty(len(need), H, W, 3)
             dist.recv(buf, src=prev, group=self.group)
-            for j, f in enumerate(need):
-                comp[pos[f]] = buf[j]
+            comp.index_copy_(0, pipe.index([pos[f] for f in need]), buf)
+            for f in need:
                 visited[f] = True
             self.last_bytes["seam_frames"] = self.last_bytes.get("seam_frames", 0)
-        ori_t = ori[touched] if touched else ori[:0]
-        md_t = md_all[touched] if touched else md_all[:0]
+        ori_t = ori[touched[0]:touched[-1] + 1] if touched else ori[:0]          # a rank's windows touch a contiguous frame range
+        md_t = md_all[touched[0]:touched[-1] + 1] if touched else md_all[:0]
         for wi in mine_w:
             nb = plan[wi][0]
             ops.composite_blend(preds[wi], md_t, ori_t, comp, [pos[i] for i in nb], [not visited[i] for i in nb])
@@ -296,17 +296,17 @@ class ShardedProPainter:
             later = {f for wi in range(len(plan)) if owner[wi] == nxt for f in plan[wi][0]}
             send = sorted(later & set(touched))
             if send:
-                sb = comp[[pos[f] for f in send]].contiguous()
+                sb = comp.index_select(0, pipe.index([pos[f] for f in send]))
                 dist.send(sb, dst=nxt, group=self.group)
                 self.last_bytes["seam_frames"] = self.last_bytes.get("seam_frames", 0) + sb.numel()
         final = [f for f in touched if sp.final_owner[f] == rank]
-        out = comp[[pos[f] for f in final]] if final else comp[:0]
+        out = comp.index_select(0, pipe.index([pos[f] for f in final])) if final else comp[:0]
         if not gather:
             return out, final
         # tests only: assemble the whole video everywhere (padded to T frames per rank)
         full = ori.new_zeros((T, H, W, 3))
         if final:
-            full[final] = out
+            full.index_copy_(0, pipe.index(final), out)
         allc = [torch.empty_like(full) for _ in range(self.world)]
         dist.all_gather(allc, full, group=self.group)
         res = torch.empty_like(full)

@@ -104,6 +104,14 @@ class ProPainterPipeline:
                                   else RecurrentFlowCompleteNet(weights[1], seed=seeds[1]).to(device))
         self.model = model if model is not None else InpaintGenerator(model_path=weights[2], seed=seeds[2]).to(device)
 
+    def index(self, ids):
+        """device int64 index tensor for a frame list, built once per distinct list (the window plan repeats every clip)"""
+        cache = self.__dict__.setdefault("_index_cache", {})
+        key = tuple(ids)
+        if key not in cache:
+            cache[key] = torch.tensor(list(ids), dtype=torch.long, device=self.device)
+        return cache[key]
+
     def state_dicts(self):
         return {"raft": self.fix_raft.fix_raft.state_dict(), "rfc": self.fix_flow_complete.state_dict(),
                 "gen": self.model.state_dict()}
@@ -167,10 +175,17 @@ class ProPainterPipeline:
         enc_all = self.model.encode(upd_frames[0], md, upd_masks[0]).permute(0, 2, 3, 1)     # pixel-major rows: cheap frame gather
         todo = [(wi, nb, refs) for wi, (nb, refs) in enumerate(plan) if windows is None or wi in windows]
 
+        um0 = upd_masks[0]
+
         def job(nb, refs):
-            ids = nb + refs
-            return lambda slot: self.model.forward_features(enc_all[ids].permute(0, 3, 1, 2), (pred_flows[0][0, nb[:-1]], pred_flows[1][0, nb[:-1]]),
-                                                            md[ids], upd_masks[0, ids], len(nb), slot=slot)
+            # frame selections as cached device index tensors / slices: indexing with a Python list builds the index on the
+            # host and copies it with a blocking cudaMemcpy, which stalls the issuing thread until the stream has drained
+            # (measured: generate() blocked the host for the whole clip, so nothing could be queued behind it)
+            idx = self.index(nb + refs)
+            a, b = nb[0], nb[-1]                                   # neighbour frames are a contiguous range
+            return lambda slot: self.model.forward_features(enc_all.index_select(0, idx).permute(0, 3, 1, 2),
+                                                            (pred_flows[0][0, a:b], pred_flows[1][0, a:b]),
+                                                            md.index_select(0, idx), um0.index_select(0, idx), len(nb), slot=slot)
 
         def consume(k, pred):
             nb = todo[k][1]
