@@ -533,6 +533,7 @@ def run_ours(args, wl):
         for k, v in autotune.choices().items():                    # which measured plan each step replays (stderr, not the line)
             plans.setdefault(f"{k[0]}[{v}]", []).append(str(k[1:3]))
         print("autotune plans:", {k: (len(v), v[:4]) for k, v in plans.items()}, file=sys.stderr)
+        print("graph-timed plan candidates (ms):", {f"{k[0][0]}{k[0][1:]}#{k[1]}": round(v, 3) for k, v in autotune._timings.items()}, file=sys.stderr)
         try:
             line["roofline"] = roofline_probe(torch, pipe, wl)
             for o in line["roofline"].pop("others", []):           # flat top-level copies (nested lists get dropped by parsers)

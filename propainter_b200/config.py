@@ -11,8 +11,9 @@ FUSED_EPILOGUE  conv bias + activation through pp_bias_act (one pass) instead of
 UMMA_CONV       the convolutions of the two recurrent propagation scans (offset nets, backbones, deformable-conv GEMM) run on
                 the tcgen05 implicit-GEMM kernel pp_conv2d_umma (TF32 products, fused bias / activation / residual / concat
                 epilogue) instead of cuDNN + pp_bias_act + the mma.sync deform kernel.  True / False force one plan;
-                "auto" (default) times both plans of a scan once per shape during graph warm-up (autotune.pick) and replays
-                the faster one.  Environment: PP_UMMA_CONV=1|0|auto.
+                "hybrid" keeps the library convs and replaces only the deformable conv by pp_deform_gather + a 1x1
+                pp_conv2d_umma GEMM; "auto" (default) times the three plans of a scan once per shape during graph warm-up
+                (autotune.pick) and replays the fastest.  Environment: PP_UMMA_CONV=1|0|hybrid|auto.
 AUTOTUNE        time numerically equivalent plans of a step once per shape during warm-up and keep the faster
                 (propainter_b200/autotune.py): grouped conv vs per-group dense convs, conv + pp_bias_act vs cuDNN's fused
                 conv-bias-ReLU.
@@ -28,7 +29,7 @@ CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
 _u = os.environ.get("PP_UMMA_CONV", "auto")
-UMMA_CONV = "auto" if _u == "auto" else (_u != "0")
+UMMA_CONV = _u if _u in ("auto", "hybrid") else (_u != "0")
 
 
 @contextlib.contextmanager

@@ -114,9 +114,11 @@ class InpaintGenerator(ParamNet):
         return conv(x, self._wb("decoder.6"), 1, 1)
 
     # ------------------------------------------------------------------ learnable feature propagation
-    def _feat_propagation(self, x, dsf, dsb, pmask, interpolation):
+    def _feat_propagation(self, x, dsf, dsb, pmask, interpolation, gather_gemm=False):
         """BidirectionalPropagation(128, learnable=True).forward propainter.py:104-190.
-        x [lt,h,w,128] pixel-major; dsf/dsb [lt-1,h,w,2]; pmask [lt,h,w,2] -> fused [lt,128,h,w]."""
+        x [lt,h,w,128] pixel-major; dsf/dsb [lt-1,h,w,2]; pmask [lt,h,w,2] -> fused [lt,128,h,w].
+        gather_gemm: the deformable conv as pp_deform_gather + one 1x1 tcgen05 GEMM over the sampled columns instead of
+        the tap pre-pass + split-K mma.sync kernel + reduce (the library convs around it stay)."""
         if interpolation != "bilinear":
             raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
         lt, h, w, C = x.shape
@@ -131,6 +133,9 @@ class InpaintGenerator(ParamNet):
             order = list(range(lt))[::-1] if bwd else list(range(lt))
             dst = torch.empty(lt, h, w, C, device=dev)
             dw, db = self._dcn(name)
+            if gather_gemm:
+                dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(self.P[f"{fp}deform_align.{name}.weight"]))
+                cols = torch.empty(1, h, w, 9 * C, device=dev)
             prev = None
             for i, idx in enumerate(order):
                 if i == 0:
@@ -144,7 +149,11 @@ class InpaintGenerator(ParamNet):
                     o = conv(o, self._wb(p + "4"), 1, 1, act="leaky", slope=0.1)
                     w6, b6 = self._wb(p + "6")
                     o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
-                    ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C], o_bias=b6)
+                    if gather_gemm:
+                        ops.deform_gather(prev[None], o, fprop[None], 3.0, cols, o_bias=b6)
+                        ops.conv_umma([cols], dwp, 1, 1, C, bias=db, out=bb[:, :, :, C:2 * C])
+                    else:
+                        ops.deform_align(prev, o[0], fprop, 3.0, dw, db, bb[0, :, :, C:2 * C], o_bias=b6)
                 y = conv(as_nchw(bb), self._wb(f"{fp}backbone.{name}.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2)
                 # feat(idx) = aligned + backbone(...) (:173-176): bias, residual add and placement in one epilogue pass
                 conv(y, self._wb(f"{fp}backbone.{name}.2"), 1, 1, res=as_nchw(bb[:, :, :, C:2 * C]), out=as_nchw(dst[idx:idx + 1]))
@@ -302,10 +311,13 @@ class InpaintGenerator(ParamNet):
         if interpolation != "bilinear":
             raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
         xl = enc_pm[:lt]
-        if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
+        if config.UMMA_CONV == "auto":      # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
             local = autotune.pick(("gen_prop", tuple(xl.shape[1:])), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
-                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation)),
+                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation),
+                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation, True)),
                                   xl, dsf, dsb, pmask, reps=2, graph_timed=True)
+        elif config.UMMA_CONV == "hybrid":
+            local = self._feat_propagation(xl, dsf, dsb, pmask, interpolation, True)
         elif config.UMMA_CONV:
             local = self._feat_propagation_umma(xl, dsf, dsb, pmask)
         else:

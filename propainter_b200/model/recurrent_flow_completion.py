@@ -74,8 +74,9 @@ class RecurrentFlowCompleteNet(ParamNet):
     def _up2_conv(self, key, x, act="none", res=None):
         return conv(up2(x), self._w2d(key + ".conv"), 1, 1, act=act, slope=0.2, res=res)
 
-    def _propagate(self, x):
-        """BidirectionalPropagation.forward :67-124.  x [t,128,h,w] channels_last -> same."""
+    def _propagate(self, x, gather_gemm=False):
+        """BidirectionalPropagation.forward :67-124.  x [t,128,h,w] channels_last -> same.
+        gather_gemm: deformable conv = pp_deform_gather + one 1x1 tcgen05 GEMM (library convs around it unchanged)."""
         t, c, h, w = x.shape
         dev = x.device
         xs = as_pm(x)                                                         # [t,h,w,128]
@@ -93,6 +94,9 @@ class RecurrentFlowCompleteNet(ParamNet):
                 fall[..., c:2 * c] = results["backward_"]
             fall[order[0], :, :, -c:] = 0                                     # step 0 propagates the zero state
             dw, db = self._dcn(name)
+            if gather_gemm:
+                dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(self.P[f"{fp}deform_align.{name}.weight"]))
+                cols = torch.empty(1, h, w, 9 * 256, device=dev)
             for i, idx in enumerate(order):
                 pslot = fall[idx:idx + 1, :, :, -c:]                          # [1,h,w,128] view, pixel stride k*128
                 if i > 0:
@@ -103,7 +107,11 @@ class RecurrentFlowCompleteNet(ParamNet):
                     o = conv(o, self._w2d(f"{fp}deform_align.{name}.conv_offset.4"), 1, 1, act="leaky", slope=0.1)
                     w6, b6 = self._w2d(f"{fp}deform_align.{name}.conv_offset.6")
                     o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap-decoding pre-pass
-                    ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, pslot[0], o_bias=b6)
+                    if gather_gemm:
+                        ops.deform_gather(buf[:, :, :, :256], o, None, 5.0, cols, o_bias=b6)
+                        ops.conv_umma([cols], dwp, 1, 1, c, bias=db, out=pslot)
+                    else:
+                        ops.deform_align(buf[0, :, :, :256], o[0], None, 5.0, dw, db, pslot[0], o_bias=b6)
                 y = conv(as_nchw(fall[idx:idx + 1]), self._w2d(f"{fp}backbone.{name}.0"), 1, 1, act="leaky", slope=0.1)
                 # state(i) = aligned + backbone(...) (:108-110): bias, residual add and placement in one epilogue pass
                 conv(y, self._w2d(f"{fp}backbone.{name}.2"), 1, 1, res=as_nchw(pslot), out=as_nchw(hist[i + 2:i + 3]))
@@ -193,7 +201,10 @@ class RecurrentFlowCompleteNet(ParamNet):
         for i, d in ((0, 3), (2, 2), (4, 1)):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
         if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
-            fpr = autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate), m, reps=2, graph_timed=True)
+            fpr = autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate, lambda a: self._propagate(a, True)),
+                                m, reps=2, graph_timed=True)
+        elif config.UMMA_CONV == "hybrid":
+            fpr = self._propagate(m, True)
         else:
             fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
         d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
