@@ -260,10 +260,13 @@ def roofline_probe(torch, pipe, wl):
 
     Primary entry = the tensor-core kernel the north star names (sparse window attention, tcgen05/TMEM); the
     `others` list carries the HBM-bound RAFT lookup and the deformable alignment.  ncu DRAM traffic figures
-    (`traffic`) come from the committed capture profiles/r1_ncu_final_kernels.csv (dram read + write per launch; the
-    lookup figure is the 22-pair capture scaled to the batch; they cannot be measured outside a profiler)."""
+    (`traffic`, bytes per launch) come from the committed capture profiles/r2_ncu_kernels.csv (dram__bytes_read.sum +
+    dram__bytes_write.sum of one `ncu --set full` pass over profiles/ncu_targets.py at these shapes; the lookup figure is the
+    22-pair capture scaled to the batch; they cannot be measured outside a profiler and are only attached at the C2 shapes)."""
     from propainter_b200 import ops
     from propainter_b200.window_index import padded_grid, token_grid, window_key_table
+    c2 = (wl["H"], wl["W"]) == (240, 432)
+    ncu = (lambda mb: int(mb * 1e6)) if c2 else (lambda mb: None)
     hbm, bf16, src = peaks()
     tf32_peak = bf16 / 2.0                                          # tcgen05 kind::tf32 runs at half the bf16 rate
     dev = pipe.device
@@ -284,7 +287,7 @@ def roofline_probe(torch, pipe, wl):
     ms = _time_kernel(torch, lambda: ops.sparse_window_attn(qkv, pool, ktab, flags, t, H2 * W2, 0, 2))
     ach = flops / (ms * 1e-3) / 1e12
     primary = {"kernel": "k_sparse_attn_umma (+ unmasked-window kernel)", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None, "peak_source": src + " bf16_tflops / 2 (TF32)",
+               "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": ncu(29.62 + 0.21), "peak_source": src + " bf16_tflops / 2 (TF32)",
                "launch_ms": ms, "algorithmic_flops": flops, "masked_windows": f"{nmask} of {nwin}"}
     # ---- RAFT correlation lookup, one refinement step of the whole clip
     h, w = wl["H"] // 8, wl["W"] // 8
@@ -318,18 +321,18 @@ def roofline_probe(torch, pipe, wl):
     fl_c = Hh * Ww * 9 * 128 * 128 * 2
     primary["others"] = [
         {"key": "corr_lookup", "kernel": "k_corr_lookup_tma", "bound": "hbm", "achieved": ach_l, "peak": hbm, "unit": "GB/s", "frac": ach_l / hbm,
-         "traffic": None, "launch_ms": ms_l, "algorithmic_bytes": alg},
+         "traffic": ncu((107.34 + 18.49) * B / 22.0), "launch_ms": ms_l, "algorithmic_bytes": alg},
         {"key": "deform", "kernel": "k_deform_gather + k_conv_umma (1x1 over the sampled columns)", "bound": "tensor",
          "achieved": fl_d / ((ms_g + ms_m) * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-         "frac": fl_d / ((ms_g + ms_m) * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_g + ms_m, "gather_ms": ms_g, "gemm_ms": ms_m,
+         "frac": fl_d / ((ms_g + ms_m) * 1e-3) / 1e12 / tf32_peak, "traffic": ncu(14.60 + 0.03 + 30.52 + 0.02), "launch_ms": ms_g + ms_m, "gather_ms": ms_g, "gemm_ms": ms_m,
          "algorithmic_flops": fl_d, "note": "two launches; the gather is L2-bandwidth bound (119 MB of corner reads per step)"},
         {"key": "conv", "kernel": "k_conv_umma 3x3 128->128 on the 60x108 map", "bound": "tensor", "achieved": fl_c / (ms_c * 1e-3) / 1e12,
-         "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl_c / (ms_c * 1e-3) / 1e12 / tf32_peak, "traffic": None, "launch_ms": ms_c,
+         "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl_c / (ms_c * 1e-3) / 1e12 / tf32_peak, "traffic": ncu(10.61), "launch_ms": ms_c,
          "algorithmic_flops": fl_c, "note": "single launch incl. launch latency; 112 CTAs on 148 SMs; tf32 operands from shared memory"}]
     return primary
 
 
-def strong_block(torch, dist, pipe, dev, rank, world, steps=2, warmup=1):
+def strong_block(torch, dist, pipe, dev, rank, world, steps=1, warmup=1):
     """One long clip (STRONG_WORKLOAD) cooperatively: every rank holds the uint8 clip + masks, computes its shard of every
     stage and exchanges halos point to point; device-timed, max over ranks.  world == 1: the plain single-GPU pipeline."""
     from propainter_b200 import synth
@@ -365,7 +368,7 @@ def strong_block(torch, dist, pipe, dev, rank, world, steps=2, warmup=1):
         dist.all_reduce(sent, op=dist.ReduceOp.SUM)
     out = {"workload": wl["name"], "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
            "value": wl["T"] * steps / (t.item() * 1e-3), "unit": "frames/s", "ms_per_clip": t.item() / steps,
-           "p2p_bytes_per_clip": sent.item(),
+           "p2p_bytes_per_clip": sent.item(), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
            "exchange": "batched point-to-point (NCCL send/recv) of raw / completed flows, propagated frames, encoder features of "
                        "neighbour + reference frames, uint8 seam frames; no collective on the data path"}
     if runner is not None and rank == 0:
@@ -505,13 +508,6 @@ def run_ours(args, wl):
         ms_total, launches, clocks = timed(step_resident, args.steps, args.warmup, True)
         ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
     strong = None
-    if not args.no_strong and not shard and args.workload == "c2":
-        try:
-            strong = strong_block(torch, dist, pipe, dev, rank, world)
-        except Exception as exc:                                   # never lose the headline line to the extra block
-            strong = {"error": repr(exc)}
-            if world > 1:
-                raise
     frames_total = wl["T"] * (1 if shard else world) * args.steps
     if rank == 0:
         line = {
@@ -542,8 +538,6 @@ def run_ours(args, wl):
             line["roofline"] = {"error": repr(exc)}
         if single is not None:
             line["single_clip"] = single
-        if strong is not None:
-            line["strong"] = strong
         if world == 1 and not args.no_gpu_reference:
             try:                                                   # the >= 10x target's denominator, same box, same clip
                 torch.cuda.empty_cache()
@@ -551,6 +545,24 @@ def run_ours(args, wl):
                 line["gpu_reference"]["speedup_e2e"] = line["e2e"]["value"] / line["gpu_reference"]["no_empty_cache"]["value"]
             except Exception as exc:
                 line["gpu_reference"] = {"error": repr(exc)}
+    if not args.no_strong and not shard and args.workload == "c2":
+        # last GPU block: its engine (own graph caches) is dropped afterwards.  Every rank takes part.
+        try:
+            import gc
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            spipe = ProPainterPipeline(device=dev)
+            strong = strong_block(torch, dist, spipe, dev, rank, world)
+            del spipe
+            gc.collect()
+            torch.cuda.empty_cache()
+        except Exception as exc:                                   # never lose the headline line to the extra block
+            strong = {"error": repr(exc)}
+            if world > 1:
+                raise
+    if rank == 0:
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))

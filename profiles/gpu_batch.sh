@@ -1,15 +1,5 @@
 mkdir -p gpurun_out
-B="timeout 400 python bench.py --steps 6 --warmup 3 --no-strong --no-gpu-reference --no-cpu-baseline"
-run() { name=$1; shift; "$@" > gpurun_out/$name.log 2> gpurun_out/$name.err; python - <<PY
-import json
-for l in open("gpurun_out/$name.log"):
-    if l.startswith("{"):
-        d = json.loads(l); print("$name", round(d["value"], 1), "fps", round(d["ms_per_step"], 1), "ms e2e", round(d["e2e"]["value"], 1), d.get("single_clip"))
-PY
-grep "graph-timed\|Error\|error" gpurun_out/$name.err | cut -c1-600; }
-run b_hybrid $B
-export CUDA_DEVICE_MAX_CONNECTIONS=32
-run b_conn32 $B
-run b_conn32_c2 $B --clips-in-flight 2
-run b_conn32_w5 $B --windows-in-flight 5
-run b_conn32_c3 $B --clips-in-flight 3
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+( time timeout 600 python bench.py --no-cpu-baseline ) > gpurun_out/bench_1gpu.log 2> gpurun_out/bench_1gpu.err; tail -c 2500 gpurun_out/bench_1gpu.log; tail -4 gpurun_out/bench_1gpu.err | cut -c1-300
+timeout 600 $TR profiles/dist_check.py 33 10 > gpurun_out/dist_check_2gpu.log 2>&1; grep -v "^W\|warn" gpurun_out/dist_check_2gpu.log | tail -6
+( time timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 3 ) > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err; tail -c 3500 gpurun_out/bench_2gpu.log; tail -4 gpurun_out/bench_2gpu.err | cut -c1-300

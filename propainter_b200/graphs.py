@@ -34,6 +34,10 @@ class GraphCache:
         Returned tensors are fresh clones, so callers may keep them across replays."""
         if not (self.enabled and config.CUDA_GRAPHS) or not inputs[0].is_cuda:
             return fn(*inputs)
+        if sum(x.numel() * x.element_size() for x in inputs) > config.GRAPH_MAX_INPUT_BYTES:
+            # a capture pins its whole working set in a private pool; at 720p+ that is tens of GB per stage shape (a
+            # 300-frame 720p clip pinned 150 GB) while the kernels are long enough for eager launches to keep up
+            return fn(*inputs)
         key = (key, _switches()) + tuple((tuple(x.shape), x.dtype, x.device.index) for x in inputs)
         e = self.entries.pop(key, None)
         if e is not None:
