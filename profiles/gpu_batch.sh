@@ -1,5 +1,14 @@
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-( time timeout 600 python bench.py --no-cpu-baseline ) > gpurun_out/bench_1gpu.log 2> gpurun_out/bench_1gpu.err; tail -c 2500 gpurun_out/bench_1gpu.log; tail -4 gpurun_out/bench_1gpu.err | cut -c1-300
-timeout 600 $TR profiles/dist_check.py 33 10 > gpurun_out/dist_check_2gpu.log 2>&1; grep -v "^W\|warn" gpurun_out/dist_check_2gpu.log | tail -6
-( time timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 3 ) > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err; tail -c 3500 gpurun_out/bench_2gpu.log; tail -4 gpurun_out/bench_2gpu.err | cut -c1-300
+B="timeout 400 python bench.py --steps 6 --warmup 3 --no-strong --no-gpu-reference --no-cpu-baseline"
+run() { name=$1; shift; "$@" > gpurun_out/$name.log 2> gpurun_out/$name.err; python - <<PY
+import json
+for l in open("gpurun_out/$name.log"):
+    if l.startswith("{"):
+        d = json.loads(l); print("$name", round(d["value"], 1), "fps", round(d["ms_per_step"], 1), "ms e2e", round(d["e2e"]["value"], 1), d.get("single_clip"), d["clocks"])
+PY
+grep "Error\|error" gpurun_out/$name.err | cut -c1-600; }
+run p0_c1 $B
+export PP_SCAN_PRIORITY=1
+run p1_c1 $B
+run p1_c2 $B --clips-in-flight 2
+run p1_c3 $B --clips-in-flight 3

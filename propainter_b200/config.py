@@ -14,6 +14,8 @@ UMMA_CONV       the convolutions of the two recurrent propagation scans (offset 
                 "hybrid" keeps the library convs and replaces only the deformable conv by pp_deform_gather + a 1x1
                 pp_conv2d_umma GEMM; "auto" (default) times the three plans of a scan once per shape during graph warm-up
                 (autotune.pick) and replays the fastest.  Environment: PP_UMMA_CONV=1|0|hybrid|auto.
+SCAN_PRIORITY   capture the recurrent propagation scans as high-priority branches of their stage graphs (graphs.high_priority).
+                Environment: PP_SCAN_PRIORITY=0|1.
 GRAPH_MAX_INPUT_BYTES  stage calls whose inputs exceed this run eagerly instead of as a captured graph (memory: a capture keeps
                 its whole working set alive in a private pool).
 AUTOTUNE        time numerically equivalent plans of a step once per shape during warm-up and keep the faster
@@ -31,6 +33,7 @@ CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
 GRAPH_MAX_INPUT_BYTES = 512 << 20
+SCAN_PRIORITY = os.environ.get("PP_SCAN_PRIORITY", "0") != "0"
 _u = os.environ.get("PP_UMMA_CONV", "auto")
 UMMA_CONV = _u if _u in ("auto", "hybrid") else (_u != "0")
 

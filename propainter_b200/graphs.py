@@ -13,8 +13,31 @@ from . import config, ops
 
 def _switches():
     """execution switches that are baked into a capture: part of the cache key, so flipping one re-captures"""
-    return (config.LINEAR_TF32, config.FUSED_EPILOGUE, config.AUTOTUNE, config.CUDNN_BENCHMARK, config.UMMA_CONV,
+    return (config.LINEAR_TF32, config.FUSED_EPILOGUE, config.AUTOTUNE, config.CUDNN_BENCHMARK, config.UMMA_CONV, config.SCAN_PRIORITY,
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+
+_hp_streams = {}
+
+
+def high_priority(fn):
+    """Run fn() as a high-priority branch of the graph being captured (fork / join around it); outside a capture, or with
+    config.SCAN_PRIORITY off, just call it.  Kernel nodes keep the priority of the stream they were captured on.  Used for
+    the recurrent propagation scans: chains of small dependent kernels that otherwise queue behind the not yet dispatched
+    CTAs of the big kernels other windows / clips have in flight (the work distributor hands out a kernel's CTAs in launch
+    order within one priority level)."""
+    if not (config.SCAN_PRIORITY and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        return fn()
+    cur = torch.cuda.current_stream()
+    key = (cur.device_index, cur.stream_id)
+    hp = _hp_streams.get(key)
+    if hp is None:
+        hp = _hp_streams[key] = torch.cuda.Stream(device=cur.device, priority=-1)
+    hp.wait_stream(cur)
+    with torch.cuda.stream(hp):
+        out = fn()
+    cur.wait_stream(hp)
+    return out
 
 
 class GraphCache:

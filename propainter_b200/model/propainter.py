@@ -10,6 +10,7 @@ import torch.nn.functional as F
 
 from .. import autotune, config, ops
 from .._params import ParamNet
+from ..graphs import high_priority
 from ..nn_util import as_nchw, as_pm, cl, conv, pad_in_channels, up2
 from ..schemas import generator_schema
 from ..window_index import padded_grid, token_grid
@@ -311,17 +312,19 @@ class InpaintGenerator(ParamNet):
         if interpolation != "bilinear":
             raise NotImplementedError("the feature propagation path uses bilinear warping (propainter.py:319 default)")
         xl = enc_pm[:lt]
-        if config.UMMA_CONV == "auto":      # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
-            local = autotune.pick(("gen_prop", tuple(xl.shape[1:])), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
-                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation),
-                                                                  lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation, True)),
-                                  xl, dsf, dsb, pmask, reps=2, graph_timed=True)
-        elif config.UMMA_CONV == "hybrid":
-            local = self._feat_propagation(xl, dsf, dsb, pmask, interpolation, True)
-        elif config.UMMA_CONV:
-            local = self._feat_propagation_umma(xl, dsf, dsb, pmask)
-        else:
-            local = self._feat_propagation(xl, dsf, dsb, pmask, interpolation)
+
+        def scan():
+            if config.UMMA_CONV == "auto":  # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
+                return autotune.pick(("gen_prop", tuple(xl.shape[1:])), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
+                                                                          lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation),
+                                                                          lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation, True)),
+                                     xl, dsf, dsb, pmask, reps=2, graph_timed=True)
+            if config.UMMA_CONV == "hybrid":
+                return self._feat_propagation(xl, dsf, dsb, pmask, interpolation, True)
+            if config.UMMA_CONV:
+                return self._feat_propagation_umma(xl, dsf, dsb, pmask)
+            return self._feat_propagation(xl, dsf, dsb, pmask, interpolation)
+        local = high_priority(scan)
         enc2 = torch.cat([local, enc[lt:]], 0).contiguous(memory_format=torch.channels_last)
         tok_in = self.tx.soft_split(enc2)
         tok = self.tx.run(tok_in, (h, w), flags, t_dilation)

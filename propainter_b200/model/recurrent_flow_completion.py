@@ -14,6 +14,7 @@ import torch.nn.functional as F
 
 from .. import autotune, config, ops
 from .._params import ParamNet
+from ..graphs import high_priority
 from ..nn_util import as_nchw, as_pm, cl, conv, up2
 from ..schemas import rfc_schema
 
@@ -200,13 +201,15 @@ class RecurrentFlowCompleteNet(ParamNet):
         m = e2
         for i, d in ((0, 3), (2, 2), (4, 1)):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
-        if config.UMMA_CONV == "auto":      # two plans of the same scan (both TF32 tensor-core products): keep the faster one for this shape
-            fpr = autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate, lambda a: self._propagate(a, True)),
-                                m, reps=2, graph_timed=True)
-        elif config.UMMA_CONV == "hybrid":
-            fpr = self._propagate(m, True)
-        else:
-            fpr = self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
+
+        def scan():
+            if config.UMMA_CONV == "auto":  # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
+                return autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate, lambda a: self._propagate(a, True)),
+                                     m, reps=2, graph_timed=True)
+            if config.UMMA_CONV == "hybrid":
+                return self._propagate(m, True)
+            return self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)
+        fpr = high_priority(scan)
         d2 = self._up2_conv("decoder2.2", conv(fpr, self._w2d("decoder2.0"), 1, 1, act="leaky", slope=0.2), "leaky", res=e1)
         d1 = self._up2_conv("decoder1.2", conv(d2, self._w2d("decoder1.0"), 1, 1, act="leaky", slope=0.2), "leaky")
         fl = self._up2_conv("upsample.2", conv(d1, self._w2d("upsample.0"), 1, 1, act="leaky", slope=0.2))
