@@ -238,6 +238,74 @@ class InpaintGenerator(ParamNet):
               bias=self._ub(fp + "fuse.0"), act="leaky", slope=0.2, round_tf32=True)
         return as_nchw(U([z], self._uw(fp + "fuse.2", ((0, C),), (C,)), 3, 3, C, bias=self._ub(fp + "fuse.2"), res=x))
 
+    def _lw(self, key, sel, bias=True):
+        """(channels_last conv weight, bias | None) of conv `key` restricted to input channels `sel`: list of (lo, hi) ranges
+        of the original weight, or ("zero", n) for n zero-weight pad channels, concatenated in that order."""
+        def build():
+            w = self.P[key + ".weight"]
+            parts = [w.new_zeros(w.shape[0], s[1], *w.shape[2:]) if s[0] == "zero" else w[:, s[0]:s[1]] for s in sel]
+            return cl(torch.cat(parts, 1)), (self.P[key + ".bias"].contiguous() if bias else None)
+        return self.packed(f"lw:{key}:{sel}:{bias}", build)
+
+    def _feat_propagation_hoisted(self, x, dsf, dsb, pmask):
+        """`_feat_propagation` with the algebra of `_feat_propagation_umma` but library convs: conv(cat[a, b]) = conv_a(a) +
+        conv_b(b), so the shares of conv_offset.0 and backbone.0 over step-independent inputs (current frame, flow, validity,
+        mask: 133 of 261 and 130 of 258 input channels) are one batched conv per scan, and the per-step convs see only the
+        128 state-dependent channels (K = 1152 instead of 2376 / 2340); their result enters through pp_bias_act_pre.  The
+        deformable conv is pp_deform_gather + a 1x1 tcgen05 GEMM."""
+        lt, h, w, C = x.shape
+        dev = x.device
+        fp = "feat_prop_module."
+        hin = torch.zeros(lt, h, w, C + 8, device=dev)            # [cur 0:128 | fx fy valid m0 m1 0 0 0]: everything known before the scan
+        aux = hin[..., C:]
+        aux[..., 3:5] = pmask
+        warp, albuf = torch.empty(1, h, w, C, device=dev), torch.empty(1, h, w, C, device=dev)
+        cols = torch.empty(1, h, w, 9 * C, device=dev)
+        src, outs = x, {}
+        for name in ("backward_1", "forward_1"):
+            bwd = name == "backward_1"
+            order = list(range(lt))[::-1] if bwd else list(range(lt))
+            po, pb = f"{fp}deform_align.{name}.conv_offset.", f"{fp}backbone.{name}."
+            hin[..., :C] = src
+            aux[..., :3] = 0
+            if lt > 1:                                              # (fx, fy, valid) of every frame that has a flow in this direction
+                if bwd:
+                    ops.flow_warp_fbcheck(None, dsf, dsb, aux=aux[:lt - 1, :, :, :3], want_warp=False)
+                else:
+                    ops.flow_warp_fbcheck(None, dsb, dsf, aux=aux[1:, :, :, :3], want_warp=False)
+            # conv_offset.0 input = [cur 0:128 | warped 128:256 | flow 256:258 | valid 258 | mask 259:261] (propainter.py:151);
+            # backbone.0 input = [cur 0:128 | aligned 128:256 | mask 256:258] (:171)
+            pre_off = as_pm(conv(as_nchw(hin), self._lw(po + "0", ((0, C), (2 * C, 2 * C + 5), ("zero", 3))), 1, 1))
+            pre_bb = as_pm(conv(as_nchw(hin), self._lw(pb + "0", ((0, C), ("zero", 3), (2 * C, 2 * C + 2), ("zero", 3))), 1, 1))
+            dst = torch.empty(lt, h, w, C, device=dev)
+            dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(self.P[f"{fp}deform_align.{name}.weight"]))
+            dbias = self.P[f"{fp}deform_align.{name}.bias"]
+            prev = None
+            for i, idx in enumerate(order):
+                if i == 0:
+                    al = src[idx:idx + 1]                            # feat_prop = feat_current (:141-143)
+                else:
+                    fprop = (dsf[idx] if bwd else dsb[idx - 1])[None]
+                    ops.flow_warp_fbcheck(prev, fprop, warped=warp)
+                    o = conv(as_nchw(warp), self._lw(po + "0", ((C, 2 * C),), False), 1, 1, act="leaky", slope=0.1,
+                             pre=as_nchw(pre_off[idx:idx + 1]))
+                    o = conv(o, self._wb(po + "2"), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._wb(po + "4"), 1, 1, act="leaky", slope=0.1)
+                    w6, b6 = self._wb(po + "6")
+                    o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap decoding
+                    ops.deform_gather(prev, o, fprop, 3.0, cols, o_bias=b6)
+                    al = ops.conv_umma([cols], dwp, 1, 1, C, bias=dbias, out=albuf)
+                y = conv(as_nchw(al), self._lw(pb + "0", ((C, 2 * C),), False), 1, 1, act="leaky", slope=0.2,
+                         pre=as_nchw(pre_bb[idx:idx + 1]))
+                # feat(idx) = aligned + backbone(...) (:173-176)
+                conv(y, self._wb(pb + "2"), 1, 1, res=as_nchw(al), out=as_nchw(dst[idx:idx + 1]))
+                prev = dst[idx:idx + 1]
+            outs[name] = dst
+            src = dst                                            # forward scan consumes the backward features (:138)
+        z = torch.cat([outs["backward_1"], outs["forward_1"], pmask, pmask.new_zeros(lt, h, w, 2)], -1)
+        z = conv(as_nchw(z), self._wb(fp + "fuse.0", 2 * C + 4), 1, 1, act="leaky", slope=0.2)
+        return conv(z, self._wb(fp + "fuse.2"), 1, 1, res=as_nchw(x))
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def encode(self, masked_frames, masks_in, masks_updated, chunk=40):
@@ -314,11 +382,14 @@ class InpaintGenerator(ParamNet):
         xl = enc_pm[:lt]
 
         def scan():
-            if config.UMMA_CONV == "auto":  # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
+            if config.UMMA_CONV == "auto":  # four plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
                 return autotune.pick(("gen_prop", tuple(xl.shape[1:])), (lambda a, b, c, d: self._feat_propagation_umma(a, b, c, d),
                                                                           lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation),
-                                                                          lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation, True)),
+                                                                          lambda a, b, c, d: self._feat_propagation(a, b, c, d, interpolation, True),
+                                                                          lambda a, b, c, d: self._feat_propagation_hoisted(a, b, c, d)),
                                      xl, dsf, dsb, pmask, reps=2, graph_timed=True)
+            if config.UMMA_CONV == "hoisted":
+                return self._feat_propagation_hoisted(xl, dsf, dsb, pmask)
             if config.UMMA_CONV == "hybrid":
                 return self._feat_propagation(xl, dsf, dsb, pmask, interpolation, True)
             if config.UMMA_CONV:

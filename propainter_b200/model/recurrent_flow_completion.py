@@ -180,6 +180,65 @@ class RecurrentFlowCompleteNet(ParamNet):
         return as_nchw(U([results["backward_"], results["forward_"]], self._uw(fp + "fusion", ((0, 2 * c),), (c, c)), 1, 1, c,
                          bias=P[fp + "fusion.bias"], res=xs))
 
+    def _lw(self, key, sel, bias=True):
+        """(channels_last 2-D conv weight, bias | None) of conv `key` restricted to the input channel ranges `sel`"""
+        def build():
+            w = self.P[key + ".weight"]
+            if w.dim() == 5:
+                w = w[:, :, 0]
+            return cl(torch.cat([w[:, lo:hi] for lo, hi in sel], 1)), (self.P[key + ".bias"].contiguous() if bias else None)
+        return self.packed(f"lw:{key}:{sel}:{bias}", build)
+
+    def _propagate_hoisted(self, x, gather_gemm=False):
+        """`_propagate` with library convs and the algebra of `_propagate_umma`: the shares of conv_offset.0 / backbone.0
+        over the current frame (and, in the forward scan, the finished backward features) are one batched conv per scan;
+        the per-step convs see only the state-dependent channels (K = 2304 instead of 3456, 1152 instead of 2304 / 3456)
+        and add the hoisted share through pp_bias_act_pre."""
+        t, c, h, w = x.shape
+        dev = x.device
+        xs = as_pm(x)                                                         # [t,h,w,128]
+        fp = "feat_prop_module."
+        albuf = torch.empty(1, h, w, c, device=dev)
+        zero = torch.zeros(1, h, w, c, device=dev)
+        results = {}
+        for di, name in enumerate(("backward_", "forward_")):
+            order = list(range(t))[::-1] if di == 0 else list(range(t))
+            po, pb = f"{fp}deform_align.{name}.conv_offset.", f"{fp}backbone.{name}."
+            hist = torch.zeros(t + 2, h, w, c, device=dev)                   # slots 0,1 = zero states
+            # conv_offset.0 input = [prop 0:128 | cur 128:256 | n2 256:384] (:93-96); backbone.0 input = [cur | (backward feats) | aligned] (:101-106)
+            pre_off = as_pm(conv(x, self._lw(po + "0", ((c, 2 * c),)), 1, 1))
+            k = 1 + di
+            hx = x if di == 0 else as_nchw(torch.cat([xs, results["backward_"]], -1))
+            pre_bb = as_pm(conv(hx, self._lw(pb + "0", ((0, k * c),)), 1, 1))
+            dw, db = self._dcn(name)
+            if gather_gemm:
+                dwp = self.packed("dcnu:" + name, lambda: ops.pack_deform_weight_umma(self.P[f"{fp}deform_align.{name}.weight"]))
+                cols = torch.empty(1, h, w, 9 * 2 * c, device=dev)
+            for i, idx in enumerate(order):
+                if i > 0:
+                    buf = torch.cat([hist[i + 1:i + 2], hist[i:i + 1]], -1)  # [state(i-1) | state(i-2)]
+                    o = conv(as_nchw(buf), self._lw(po + "0", ((0, c), (2 * c, 3 * c)), False), 1, 1, act="leaky", slope=0.1,
+                             pre=as_nchw(pre_off[idx:idx + 1]))
+                    o = conv(o, self._w2d(po + "2"), 1, 1, act="leaky", slope=0.1)
+                    o = conv(o, self._w2d(po + "4"), 1, 1, act="leaky", slope=0.1)
+                    w6, b6 = self._w2d(po + "6")
+                    o = as_pm(F.conv2d(o, w6, None, padding=1))             # bias folded into the tap decoding
+                    if gather_gemm:
+                        ops.deform_gather(buf, o, None, 5.0, cols, o_bias=b6)
+                        ops.conv_umma([cols], dwp, 1, 1, c, bias=db, out=albuf)
+                    else:
+                        ops.deform_align(buf[0], o[0], None, 5.0, dw, db, albuf[0], o_bias=b6)
+                    al = albuf
+                else:
+                    al = zero                                                # step 0 propagates the zero state
+                y = conv(as_nchw(al), self._lw(pb + "0", ((k * c, (k + 1) * c),), False), 1, 1, act="leaky", slope=0.1,
+                         pre=as_nchw(pre_bb[idx:idx + 1]))
+                # state(i) = aligned + backbone(...) (:108-110)
+                conv(y, self._w2d(pb + "2"), 1, 1, res=as_nchw(al), out=as_nchw(hist[i + 2:i + 3]))
+            seq = hist[2:]
+            results[name] = seq.flip(0) if di == 0 else seq
+        return conv(as_nchw(torch.cat([results["backward_"], results["forward_"]], -1)), self._w2d(fp + "fusion"), res=x)
+
     # ------------------------------------------------------------------ API
     @torch.no_grad()
     def forward(self, masked_flows, masks):
@@ -203,9 +262,12 @@ class RecurrentFlowCompleteNet(ParamNet):
             m = conv(m, self._w2d(f"mid_dilation.{i}"), 1, d, d, act="leaky", slope=0.2)
 
         def scan():
-            if config.UMMA_CONV == "auto":  # three plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
-                return autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate, lambda a: self._propagate(a, True)),
+            if config.UMMA_CONV == "auto":  # five plans of the same scan (all TF32 tensor-core products): keep the fastest for this shape
+                return autotune.pick(("rfc_prop", tuple(m.shape[1:])), (self._propagate_umma, self._propagate, lambda a: self._propagate(a, True),
+                                                                        self._propagate_hoisted, lambda a: self._propagate_hoisted(a, True)),
                                      m, reps=2, graph_timed=True)
+            if config.UMMA_CONV == "hoisted":
+                return self._propagate_hoisted(m)
             if config.UMMA_CONV == "hybrid":
                 return self._propagate(m, True)
             return self._propagate_umma(m) if config.UMMA_CONV else self._propagate(m)

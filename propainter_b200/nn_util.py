@@ -47,17 +47,19 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
-def conv(x, wb, stride=1, padding=0, dilation=1, groups=1, act="none", slope=0.0, res=None, post_relu=False, out=None):
+def conv(x, wb, stride=1, padding=0, dilation=1, groups=1, act="none", slope=0.0, res=None, post_relu=False, out=None, pre=None):
     """conv2d + bias + activation (+ residual add, + final ReLU, + placement into a channel slice `out`).
     The conv is cuDNN; everything after it is one pass of pp_bias_act over the channels-last result (cuDNN would launch
     a separate bias add_, ATen one kernel each for the activation, the residual add and the torch.cat).  `res` / `out`
-    are NCHW-logical channels_last views.  Plain conv+bias+ReLU may instead run as cuDNN's fused conv-bias-ReLU when
+    are NCHW-logical channels_last views; `pre` (same kind of view) is added before the activation (a conv share computed
+    ahead of time).  Plain conv+bias+ReLU may instead run as cuDNN's fused conv-bias-ReLU when
     that measures faster for the shape (autotune.pick).  Outputs whose channel count is not a multiple of 4
     (2/3-channel heads) keep the library epilogue."""
     w, b = wb
     st, pd, dl = _pair(stride), _pair(padding), _pair(dilation)
     if not (config.FUSED_EPILOGUE and w.shape[0] % 4 == 0):
-        y = _TORCH_ACT[act](F.conv2d(x, w, b, stride=st, padding=pd, dilation=dl, groups=groups), slope)
+        y = F.conv2d(x, w, b, stride=st, padding=pd, dilation=dl, groups=groups)
+        y = _TORCH_ACT[act](y if pre is None else y + pre, slope)
         if res is not None:
             y = y + res
         if post_relu:
@@ -71,10 +73,10 @@ def conv(x, wb, stride=1, padding=0, dilation=1, groups=1, act="none", slope=0.0
         y = F.conv2d(x, w, None, stride=st, padding=pd, dilation=dl, groups=groups)
         ypm = as_pm(y)
         o = ops.bias_act(ypm, b, act, slope, res=None if res is None else res.permute(0, 2, 3, 1), post_relu=post_relu,
-                         out=None if out is None else out.permute(0, 2, 3, 1))
+                         out=None if out is None else out.permute(0, 2, 3, 1), pre=None if pre is None else pre.permute(0, 2, 3, 1))
         return as_nchw(o)
 
-    if act == "relu" and res is None and out is None and not post_relu and config.AUTOTUNE:
+    if act == "relu" and res is None and out is None and pre is None and not post_relu and config.AUTOTUNE:
         def fused(x):
             return torch.cudnn_convolution_relu(x, w, b, st, pd, dl, groups).contiguous(memory_format=torch.channels_last)
         return autotune.pick(("conv_relu", tuple(x.shape), tuple(w.shape), st, pd, dl, groups), (own, fused), x)

@@ -215,6 +215,30 @@ def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pr
     return out
 
 
+def im2col_small(x, KH, KW, stride, pad, kpad, cols=None):
+    """x: NCHW-logical float tensor [n,Cin,H,W] with any strides (planar or channels_last) -> cols [n,Ho,Wo,kpad] with
+    k = c*KH*KW + ky*KW + kx, zero padded, TF32-rounded: the A operand of a 1x1 conv_umma that computes the KHxKW conv."""
+    n, Cin, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    if cols is None:
+        cols = torch.empty(n, Ho, Wo, kpad, device=x.device, dtype=torch.float32)
+    if x.dtype != torch.float32 or tuple(cols.shape) != (n, Ho, Wo, kpad):
+        raise RuntimeError("im2col_small: fp32 input and cols [n,Ho,Wo,kpad] expected")
+    sn, sc, sy, sx = x.stride()
+    check(_lib.lib().pp_im2col_small(_p(x), sn, sc, sy, sx, n, Cin, H, W, KH, KW, stride, pad, kpad, _p(_dense(cols)), _stream()),
+          "pp_im2col_small")
+    _count(1)
+    return cols
+
+
+def pack_small_conv_weight(weight, kpad):
+    """[Cout,Cin,KH,KW] -> packed 1x1 conv_umma weight over the kpad-wide patch matrix of im2col_small"""
+    co = weight.shape[0]
+    w = weight.reshape(co, -1)
+    w = torch.cat([w, w.new_zeros(co, kpad - w.shape[1])], 1)
+    return pack_conv_weight(w.reshape(co, kpad, 1, 1).contiguous())
+
+
 def deform_gather(x, o, flow, max_res, cols=None, o_bias=None, x2=None):
     """x [n,H,W,Cin] view (or, with x2, the two halves x | x2 of Cin/2 channels each), o [n,H,W,>=432] raw conv_offset
     output, flow [n,H,W,2] | None -> cols [n,H,W,9*Cin] (modulated bilinear samples, k*Cin + c, TF32-rounded): the A
@@ -365,18 +389,23 @@ def raft_pack_motion(mot_pm, flow_pm, d0_view, d1_view, bias=None):
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
 
 
-def bias_act(x_pm, bias=None, act="none", slope=0.0, res=None, post_relu=False, out=None):
-    """out = post(act(x + bias) + res) on pixel-major views [..., C] (unit channel stride, dense over pixels; x / res /
-    out may each be a channel slice of a wider buffer).  out=None -> in place on x_pm.  Returns out."""
+def bias_act(x_pm, bias=None, act="none", slope=0.0, res=None, post_relu=False, out=None, pre=None):
+    """out = post(act(x + bias + pre) + res) on pixel-major views [..., C] (unit channel stride, dense over pixels; x / pre /
+    res / out may each be a channel slice of a wider buffer).  out=None -> in place on x_pm.  Returns out."""
     C = x_pm.shape[-1]
     out = x_pm if out is None else out
-    if out.shape != x_pm.shape or (res is not None and res.shape != x_pm.shape):
+    if out.shape != x_pm.shape or (res is not None and res.shape != x_pm.shape) or (pre is not None and pre.shape != x_pm.shape):
         raise RuntimeError("bias_act: shape mismatch")
     xp, ldx = _pm(x_pm)
     op, ldo = _pm(out)
     rp, ldr = _pm(res) if res is not None else (None, C)
-    check(_lib.lib().pp_bias_act(xp, ldx, _p(bias), rp, ldr, op, ldo, x_pm.numel() // C, C, ACT[act], float(slope),
-                                 int(bool(post_relu)), _stream()), "pp_bias_act")
+    if pre is not None:
+        pp, ldp = _pm(pre)
+        check(_lib.lib().pp_bias_act_pre(xp, ldx, _p(bias), pp, ldp, rp, ldr, op, ldo, x_pm.numel() // C, C, ACT[act], float(slope),
+                                         int(bool(post_relu)), _stream()), "pp_bias_act_pre")
+    else:
+        check(_lib.lib().pp_bias_act(xp, ldx, _p(bias), rp, ldr, op, ldo, x_pm.numel() // C, C, ACT[act], float(slope),
+                                     int(bool(post_relu)), _stream()), "pp_bias_act")
     _count(1)
     return out
 

@@ -58,23 +58,31 @@ def test_flow_completion_both_conv_plans(emu, monkeypatch):
     masks = torch.zeros(1, 6, 1, 32, 48)
     masks[..., 8:24, 12:36] = 1
     ref = flowcomp_ref.forward_bidirect_flow(net.state_dict(), flows, masks)
-    for flag in (True, False, "hybrid"):                  # hybrid: library convs + gather / 1x1-GEMM deformable conv
-        monkeypatch.setattr(config, "UMMA_CONV", flag)
+    from propainter_b200 import autotune
+    # hybrid: library convs + gather / 1x1-GEMM deformable conv; hoisted: + frame-only conv shares once per scan; 3 / 4: the
+    # autotune candidates "hoisted" and "hoisted + gather/GEMM"
+    for flag in (True, False, "hybrid", "hoisted", 3, 4):
+        if isinstance(flag, int) and not isinstance(flag, bool):
+            monkeypatch.setattr(config, "UMMA_CONV", "auto")
+            monkeypatch.setattr(autotune, "pick", lambda key, variants, *a, _i=flag, **k: variants[_i if key[0] == "rfc_prop" else 0](*a))
+        else:
+            monkeypatch.setattr(config, "UMMA_CONV", flag)
         out, _ = net.forward_bidirect_flow(flows, masks)
         for k in (0, 1):
             assert rel_err(out[k], ref[k]) < 1e-4, (flag, k, rel_err(out[k], ref[k]))
 
 
 @pytest.mark.parametrize("H,W,t,lt,alt", [(64, 96, 4, 3, False), (128, 128, 3, 2, False), (64, 64, 2, 1, False), (64, 96, 4, 3, True),
-                                          (64, 96, 4, 3, "cudnn"), (64, 64, 2, 1, "cudnn"), (64, 96, 4, 3, "hybrid")])
+                                          (64, 96, 4, 3, "cudnn"), (64, 64, 2, 1, "cudnn"), (64, 96, 4, 3, "hybrid"),
+                                          (64, 96, 4, 3, "hoisted"), (64, 64, 2, 1, "hoisted")])
 def test_generator_plumbing(emu, monkeypatch, H, W, t, lt, alt):
     from propainter_b200 import autotune, config
     from propainter_b200.model.propainter import InpaintGenerator
     if alt == "cudnn":                                  # the library-conv plan of the propagation scan (config.UMMA_CONV off)
         monkeypatch.setattr(config, "UMMA_CONV", False)
         alt = False
-    if alt == "hybrid":                                 # library convs + pp_deform_gather / 1x1 pp_conv2d_umma deformable conv
-        monkeypatch.setattr(config, "UMMA_CONV", "hybrid")
+    if alt in ("hybrid", "hoisted"):                    # library convs + pp_deform_gather / 1x1 pp_conv2d_umma deformable conv
+        monkeypatch.setattr(config, "UMMA_CONV", alt)   # (hoisted: + the frame-only conv shares once per scan)
         alt = False
     if alt:      # force the alternative execution plans autotune may pick on the GPU (per-group dense encoder convs)
         monkeypatch.setattr(autotune, "pick", lambda key, variants, *a, **k: variants[0 if key[0] == "conv_relu" else -1](*a))
