@@ -171,16 +171,6 @@ int pp_gru_update(const float* q, const float* bias, const float* pre, const flo
 int pp_raft_pack_motion(const float* mot, int ld_mot, const float* bias, const float* flow, float* d0, float* d1, int ld,
                         long npix, cudaStream_t stream);
 
-/* ---- few-input-channel convolutions ------------------------------------------------------------ */
-/* Patch matrix of a KHxKW convolution (stride, zero padding `pad`) over a Cin-channel input addressed through element
- * strides (planar frames [n,C,H,W] or pixel-major maps [n,H,W,C]): cols [n*Ho*Wo][kpad], k = c*KH*KW + ky*KW + kx (the order
- * of weight.reshape(Cout, -1)), zeros for taps outside the image and for k >= Cin*KH*KW, values rounded to TF32.  With a 1x1
- * pp_conv2d_umma over K = kpad this replaces the 7x7 convs over 3 image channels (RAFT/extractor.py:125,168) and over the 2
- * flow channels (RAFT/update.py:78,92) -- K = 147 / 98, shapes the library's implicit-GEMM kernels run at ~30 TFLOP/s.
- * kpad: multiple of 4, >= Cin*KH*KW (use a multiple of 32 for the GEMM). */
-int pp_im2col_small(const float* x, long stride_n, long stride_c, long stride_y, long stride_x, int n, int Cin, int H, int W, int KH,
-                    int KW, int stride, int pad, int kpad, float* cols, cudaStream_t stream);
-
 /* ---- conv epilogues ------------------------------------------------------------------------- */
 /* out = post(act(x + bias[c]) + res) on pixel-major tensors [n_pix][C] with pixel strides ld_*: replaces the bias add of
  * F.conv2d, the ReLU / LeakyReLU / sigmoid / tanh that follows it at every conv of the three nets, the residual add

@@ -16,7 +16,7 @@ What differs is the execution plan:
 import torch
 import torch.nn.functional as F
 
-from .. import autotune, config, ops
+from .. import ops
 from .._params import ParamNet
 from ..nn_util import as_nchw, as_pm, cl, conv
 from ..schemas import raft_schema
@@ -44,19 +44,6 @@ class RAFT(ParamNet):
             return cl(w), b.contiguous()
         return self.packed("wb:" + key, build)
 
-    def _small(self, key, kpad, bn=None):
-        """(packed 1x1 pp_conv2d_umma weight over the kpad-wide patch matrix, bias) of a few-input-channel 7x7 conv"""
-        def build():
-            w, b = self._wb(key, bn)
-            return ops.pack_small_conv_weight(w.contiguous(), kpad), b
-        return self.packed(f"small:{key}:{kpad}", build)
-
-    @staticmethod
-    def _own_small_convs(x):
-        """the 7x7 convs over 2-3 input channels run as pp_im2col_small + a tcgen05 GEMM (TF32 products) unless the caller
-        asked the library for full-fp32 convolutions (torch.backends.cudnn.allow_tf32 = False)"""
-        return config.SMALL_CIN_UMMA and x.is_cuda and torch.backends.cudnn.allow_tf32
-
     def _motion_out(self):
         """update_block.encoder.conv with its 126 outputs padded to 128 (two zero filters): keeps the output
         rows 16-byte aligned; the pad slots are overwritten by the flow channels in raft_pack_motion."""
@@ -82,9 +69,8 @@ class RAFT(ParamNet):
         return self.packed("gru" + tag, build)
 
     # ------------------------------------------------------------------ encoders (extractor.py:168-192)
-    def _encode(self, p, x, stem_cols=None):
-        """BasicEncoder.forward extractor.py:168-192.  stem_cols: the patch matrix of the 7x7 stride-2 stem conv (shared by
-        fnet and cnet, ops.im2col_small) -> the stem is one 1x1 tcgen05 GEMM over it instead of a library conv.  fnet: conv -> InstanceNorm -> ReLU with the norm, the ReLU and the
+    def _encode(self, p, x):
+        """BasicEncoder.forward extractor.py:168-192.  fnet: conv -> InstanceNorm -> ReLU with the norm, the ReLU and the
         block's `relu(x + y)` as one pp_instance_norm call on the raw conv output (the conv bias cancels under the
         per-channel mean subtraction, so it is not even added).  cnet: eval BatchNorm folded into the conv; bias, ReLU
         and the residual add + ReLU are one pp_bias_act pass."""
@@ -98,15 +84,7 @@ class RAFT(ParamNet):
                                                  post_relu=res is not None, out=y))
             return conv(t, self._wb(key, bn), stride, pad, act="relu" if relu else "none", res=res, post_relu=res is not None)
 
-        if stem_cols is not None:
-            wp, b = self._small(p + ".conv1", stem_cols.shape[-1], p + ".norm1")
-            if inst:                                            # raw conv -> InstanceNorm + ReLU (the bias cancels under the mean)
-                y = ops.conv_umma([stem_cols], wp, 1, 1, 64)
-                x = as_nchw(ops.instance_norm(y, relu=True, out=y))
-            else:                                               # eval BatchNorm folded into weight / bias, ReLU in the epilogue
-                x = as_nchw(ops.conv_umma([stem_cols], wp, 1, 1, 64, bias=b, act="relu"))
-        else:
-            x = cn(p + ".conv1", p + ".norm1", x, 2, 3)
+        x = cn(p + ".conv1", p + ".norm1", x, 2, 3)
         for li, stride in ((1, 1), (2, 2), (3, 2)):
             for bi in (0, 1):
                 q = f"{p}.layer{li}.{bi}"
@@ -119,21 +97,10 @@ class RAFT(ParamNet):
 
     def encode_frames(self, frames):
         """frames [n,3,H,W] -> (fmap pixel-major [n, h*w, 256], net [n,128,h,w], inp [n,128,h,w])."""
-        frames = frames.float()
-        if self._own_small_convs(frames):
-            def own(fr):
-                cols = ops.im2col_small(fr, 7, 7, 2, 3, 160)        # K = 147 -> 5 blocks of 32; one patch matrix for both stems
-                return self._encode("fnet", None, cols), self._encode("cnet", None, cols)
-
-            def lib(fr):
-                x = fr.contiguous(memory_format=torch.channels_last)
-                return self._encode("fnet", x), self._encode("cnet", x)
-            f, c = autotune.pick(("raft_stem", tuple(frames.shape)), (own, lib), frames, reps=2)
-        else:
-            x = frames.contiguous(memory_format=torch.channels_last)
-            f, c = self._encode("fnet", x), self._encode("cnet", x)
-        fmap = as_pm(f.float())
+        x = frames.contiguous(memory_format=torch.channels_last)
+        fmap = as_pm(self._encode("fnet", x).float())
         n, h, w, d = fmap.shape
+        c = self._encode("cnet", x)
         net, inp = torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
         return fmap.view(n, h * w, d), net, inp, (h, w)
 
@@ -165,27 +132,13 @@ class RAFT(ParamNet):
         netc = torch.empty(B, h, w, 128, device=dev)            # dense copy of the state for the flow / mask heads
         mot_in = torch.empty(B, h, w, 256, device=dev)          # [cor(192) | flo(64)] without a torch.cat (update.py:95)
         mw, mb = self._motion_out()
-        own_f1 = self._own_small_convs(fmap)
-        if own_f1:                                              # convf1: 7x7 over the 2 flow channels, K = 98 -> 4 blocks of 32
-            f1w, f1b = self._small(u + "encoder.convf1", 128)
-            f1cols, f1out = torch.empty(B, h, w, 128, device=dev), torch.empty(B, h, w, 128, device=dev)
-
-            def f1_own(fl):
-                ops.im2col_small(fl, 7, 7, 1, 3, 128, cols=f1cols)
-                return as_nchw(ops.conv_umma([f1cols], f1w, 1, 1, 128, bias=f1b, act="relu", out=f1out))
-
-            def f1_lib(fl):
-                return conv(fl, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
         for _ in range(iters):
             ops.corr_lookup(levels, c1, corr)
             flow_pm = c1 - c0
             flow = as_nchw(flow_pm)
             cor = conv(as_nchw(corr), self._wb(u + "encoder.convc1"), act="relu")
             conv(cor, self._wb(u + "encoder.convc2"), 1, 1, act="relu", out=as_nchw(mot_in[..., :192]))
-            if own_f1:
-                flo = autotune.pick(("raft_convf1", (B, h, w)), (f1_own, f1_lib), flow, reps=3)
-            else:
-                flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
+            flo = conv(flow, self._wb(u + "encoder.convf1"), 1, 3, act="relu")
             conv(flo, self._wb(u + "encoder.convf2"), 1, 1, act="relu", out=as_nchw(mot_in[..., 192:]))
             mot = F.conv2d(as_nchw(mot_in), mw, None, padding=1)                   # 126 real + 2 pad channels, raw
             ops.raft_pack_motion(as_pm(mot), flow_pm, HX[..., 128:], RX[..., 128:], bias=mb)   # + bias + ReLU (update.py:96)

@@ -15,9 +15,6 @@ UMMA_CONV       the convolutions of the two recurrent propagation scans (offset 
                 pp_conv2d_umma GEMM; "hoisted" additionally convolves the step-independent input channels of
                 conv_offset.0 / backbone.0 once per scan (library convs, pp_bias_act_pre); "auto" (default) times the plans of a scan once per shape during graph warm-up
                 (autotune.pick) and replays the fastest.  Environment: PP_UMMA_CONV=1|0|hybrid|hoisted|auto.
-SMALL_CIN_UMMA  RAFT's 7x7 convs over 2-3 input channels (both stems, convf1) as pp_im2col_small + a 1x1 pp_conv2d_umma GEMM
-                when that measures faster than the library conv (autotune.pick); only with TF32 convolutions allowed
-                (torch.backends.cudnn.allow_tf32).  Environment: PP_SMALL_CIN=0|1.
 SCAN_PRIORITY   capture the recurrent propagation scans as high-priority branches of their stage graphs (graphs.high_priority).
                 Environment: PP_SCAN_PRIORITY=0|1.
 GRAPH_MAX_INPUT_BYTES  stage calls whose inputs exceed this run eagerly instead of as a captured graph (memory: a capture keeps
@@ -37,7 +34,6 @@ CUDA_GRAPHS = True
 FUSED_EPILOGUE = True
 AUTOTUNE = True
 GRAPH_MAX_INPUT_BYTES = 512 << 20
-SMALL_CIN_UMMA = os.environ.get("PP_SMALL_CIN", "1") != "0"
 SCAN_PRIORITY = os.environ.get("PP_SCAN_PRIORITY", "1") != "0"
 _u = os.environ.get("PP_UMMA_CONV", "auto")
 UMMA_CONV = _u if _u in ("auto", "hybrid", "hoisted") else (_u != "0")

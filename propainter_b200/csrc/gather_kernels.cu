@@ -172,41 +172,6 @@ extern "C" int pp_flow_warp_fbcheck(const float* feat, int ld_f, const float* fp
   return PP_OK;
 }
 
-// ================================================================ im2col for the few-input-channel 7x7 convs
-// RAFT's stems (RAFT/extractor.py:125 conv1 7x7 stride 2 over 3 image channels) and the flow branch of the motion encoder
-// (RAFT/update.py:78 convf1 7x7 over the 2 flow channels) have K = 147 / 98: cuDNN's implicit-GEMM kernels pad the 2-3 input
-// channels to their channel vector width and reach ~30 TFLOP/s on them.  This writes the patch matrix explicitly --
-// cols[pixel][k], k = c*KH*KW + ky*KW + kx (the order of weight.reshape(Cout, -1)), zero for out-of-image taps and for
-// k >= Cin*KH*KW, rounded to TF32 -- and the product runs as a 1x1 pp_conv2d_umma over K = kpad.  The input is addressed
-// through element strides, so planar frames [n,C,H,W] and pixel-major maps [n,H,W,C] both work without a copy.
-__global__ void __launch_bounds__(256) k_im2col_small(const float* __restrict__ x, long sn, long sc, long sy, long sx, int Cin, int H,
-                                                      int W, int KH, int KW, int stride, int pad, int Ho, int Wo, int kpad,
-                                                      long total, float* __restrict__ cols) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long pix = i / kpad; const int k = (int)(i - pix * kpad);
-  float v = 0.f;
-  if (k < Cin * KH * KW) {
-    const int c = k / (KH * KW); const int r = k - c * KH * KW; const int ky = r / KW, kx = r - ky * KW;
-    const long n = pix / ((long)Ho * Wo); const int q = (int)(pix - n * (long)Ho * Wo); const int oy = q / Wo, ox = q - oy * Wo;
-    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __uint_as_float(pp_tf32(__ldg(x + n * sn + c * sc + iy * sy + ix * sx)));
-  }
-  cols[i] = v;
-}
-extern "C" int pp_im2col_small(const float* x, long stride_n, long stride_c, long stride_y, long stride_x, int n, int Cin, int H, int W,
-                               int KH, int KW, int stride, int pad, int kpad, float* cols, cudaStream_t stream) {
-  if (n < 1 || Cin < 1 || H < 1 || W < 1 || KH < 1 || KW < 1 || stride < 1 || pad < 0) return PP_ERR_SHAPE;
-  if (kpad < Cin * KH * KW || kpad % 4) return PP_ERR_SHAPE;
-  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  if (Ho < 1 || Wo < 1) return PP_ERR_SHAPE;
-  const long total = (long)n * Ho * Wo * kpad;
-  k_im2col_small<<<pp_blocks(total, 256), 256, 0, stream>>>(x, stride_n, stride_c, stride_y, stride_x, Cin, H, W, KH, KW, stride, pad,
-                                                           Ho, Wo, kpad, total, cols);
-  PP_LAUNCH_CHECK();
-  return PP_OK;
-}
-
 // ================================================================ RAFT correlation pyramid + lookup
 __global__ void __launch_bounds__(256) k_corr_pool(const float* __restrict__ src, float* __restrict__ dst, long planes,
                                                    int Hs, int lds, int Hd, int Wd, int ldd) {

@@ -215,30 +215,6 @@ def conv_umma(segs, w_packed, KH, KW, Cout, bias=None, act="none", slope=0.0, pr
     return out
 
 
-def im2col_small(x, KH, KW, stride, pad, kpad, cols=None):
-    """x: NCHW-logical float tensor [n,Cin,H,W] with any strides (planar or channels_last) -> cols [n,Ho,Wo,kpad] with
-    k = c*KH*KW + ky*KW + kx, zero padded, TF32-rounded: the A operand of a 1x1 conv_umma that computes the KHxKW conv."""
-    n, Cin, H, W = x.shape
-    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
-    if cols is None:
-        cols = torch.empty(n, Ho, Wo, kpad, device=x.device, dtype=torch.float32)
-    if x.dtype != torch.float32 or tuple(cols.shape) != (n, Ho, Wo, kpad):
-        raise RuntimeError("im2col_small: fp32 input and cols [n,Ho,Wo,kpad] expected")
-    sn, sc, sy, sx = x.stride()
-    check(_lib.lib().pp_im2col_small(_p(x), sn, sc, sy, sx, n, Cin, H, W, KH, KW, stride, pad, kpad, _p(_dense(cols)), _stream()),
-          "pp_im2col_small")
-    _count(1)
-    return cols
-
-
-def pack_small_conv_weight(weight, kpad):
-    """[Cout,Cin,KH,KW] -> packed 1x1 conv_umma weight over the kpad-wide patch matrix of im2col_small"""
-    co = weight.shape[0]
-    w = weight.reshape(co, -1)
-    w = torch.cat([w, w.new_zeros(co, kpad - w.shape[1])], 1)
-    return pack_conv_weight(w.reshape(co, kpad, 1, 1).contiguous())
-
-
 def deform_gather(x, o, flow, max_res, cols=None, o_bias=None, x2=None):
     """x [n,H,W,Cin] view (or, with x2, the two halves x | x2 of Cin/2 channels each), o [n,H,W,>=432] raw conv_offset
     output, flow [n,H,W,2] | None -> cols [n,H,W,9*Cin] (modulated bilinear samples, k*Cin + c, TF32-rounded): the A

@@ -143,21 +143,6 @@ def install(monkeypatch, hostsim):
 
     _act = {"none": lambda t: t, "relu": F.relu, "leaky": None, "sigmoid": torch.sigmoid, "tanh": torch.tanh}
 
-    def im2col_small(x, KH, KW, stride, pad, kpad, cols=None):
-        n, Cin, H, W = x.shape
-        Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
-        u = F.unfold(x.contiguous(), (KH, KW), padding=pad, stride=stride).transpose(1, 2).reshape(n, Ho, Wo, Cin * KH * KW)
-        out = torch.zeros(n, Ho, Wo, kpad) if cols is None else cols
-        out.zero_()
-        out[..., :Cin * KH * KW] = u
-        return out
-
-    def pack_small_conv_weight(weight, kpad):
-        co = weight.shape[0]
-        w = weight.reshape(co, -1)
-        w = torch.cat([w, w.new_zeros(co, kpad - w.shape[1])], 1)
-        return ops.pack_conv_weight(w.reshape(co, kpad, 1, 1).contiguous())
-
     def bias_act(x_pm, bias=None, act="none", slope=0.0, res=None, post_relu=False, out=None, pre=None):
         t = x_pm if bias is None else x_pm + bias
         if pre is not None:

@@ -399,39 +399,6 @@ def test_bias_act_strided_residual_and_instance_norm():
         assert got.data_ptr() == xin.data_ptr() and torch.allclose(got, want, atol=2e-5)
 
 
-def test_small_cin_conv_via_im2col_gemm():
-    """pp_im2col_small + 1x1 pp_conv2d_umma vs F.conv2d for RAFT's few-channel 7x7 convs: the stride-2 stem over planar
-    3-channel frames (extractor.py:125) and convf1 over the pixel-major 2-channel flow (update.py:78), incl. bias + ReLU.
-    The patch matrix itself is exact (fp32 values rounded to TF32, zeros outside the image); the product is TF32: 3e-3 of
-    the output scale, and 2e-5 against an fp64 conv over the same TF32-rounded operands."""
-    from propainter_b200 import ops
-    g = torch.Generator().manual_seed(11)
-    for (n, Cin, H, W, Cout, stride, kpad, planar) in ((3, 3, 40, 56, 64, 2, 160, True), (2, 2, 30, 54, 128, 1, 128, False),
-                                                       (1, 3, 17, 23, 64, 2, 160, False)):
-        x = torch.randn(n, Cin, H, W, generator=g)
-        w = torch.randn(Cout, Cin, 7, 7, generator=g) * 0.1
-        b = torch.randn(Cout, generator=g)
-        xd = x.to(DEV) if planar else x.to(DEV).contiguous(memory_format=torch.channels_last)
-        cols = ops.im2col_small(xd, 7, 7, stride, 3, kpad)
-        ref_cols = F.unfold(x, 7, padding=3, stride=stride)                      # [n, Cin*49, L], k = c*49 + ky*7 + kx
-        Ho, Wo = cols.shape[1:3]
-        ref_cols = ref_cols.transpose(1, 2).reshape(n, Ho, Wo, Cin * 49)
-        got_cols = cols.cpu()
-        assert torch.equal(got_cols[..., Cin * 49:], torch.zeros_like(got_cols[..., Cin * 49:]))
-        assert torch.allclose(got_cols[..., :Cin * 49], ref_cols, rtol=1e-3, atol=0) and \
-            torch.equal(got_cols[..., :Cin * 49] == 0, ref_cols == 0)          # TF32 rounding only; padding zeros in place
-        wp = ops.pack_small_conv_weight(w.to(DEV), kpad)
-        out = ops.conv_umma([cols], wp, 1, 1, Cout, bias=b.to(DEV), act="relu").cpu()
-        ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=3)).permute(0, 2, 3, 1)
-        wr = ops.tf32_round(w.to(DEV)).cpu().double()
-        exact = F.relu(F.conv2d(F.fold(got_cols[..., :Cin * 49].reshape(n, Ho * Wo, -1).transpose(1, 2).double(), (1, 1), 1)
-                                .reshape(n, Cin * 49, Ho, Wo), wr.reshape(Cout, Cin * 49, 1, 1), b.double())).permute(0, 2, 3, 1)
-        scale = ref.abs().max().item()
-        e_plain, e_exact = (out - ref).abs().max().item() / scale, (out.double() - exact).abs().max().item() / scale
-        print(f"small-cin conv n={n} Cin={Cin} {H}x{W} s{stride}: vs fp32 {e_plain:.2e}  vs fp64-on-tf32 {e_exact:.2e}")
-        assert e_plain < 3e-3 and e_exact < 2e-5
-
-
 def test_transformer_glue_kernels():
     """pp_pool_depthwise vs F.conv2d(groups=C, kernel=stride) (sparse_transformer.py:131-133) and pp_add_layernorm vs
     x + d followed by F.layer_norm (:322-334); fp32, 1e-5."""
