@@ -38,7 +38,9 @@ def _worker(rank, world, port, T, sub, out_path):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     u8, fm, md = synth.make_clip(T, 128, 128, mask="ellipse", seed=0)
     pipe = ProPainterPipeline(device="cpu")                       # same seeds on every rank -> identical weights
-    cfg = InferenceConfig(raft_iter=1, subvideo_length=sub)
+    # raft_clip_frames=3: every rank's pair range goes through several RAFT chunks (the correlation-volume memory cap of
+    # compute_flows applies inside a shard as well)
+    cfg = InferenceConfig(raft_iter=1, subvideo_length=sub, raft_clip_frames=3 if world == 2 else None)
     sp = ShardedProPainter(pipe)
     sharded = sp(torch.from_numpy(u8), fm, md, cfg, gather=True)
     part, ids = sp(torch.from_numpy(u8), fm, md, cfg)            # the sharded result: this rank's final frames only
