@@ -1,2 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -k regex:'k_conv_umma|k_deform_gather|k_sparse_attn_umma|k_attn_unmasked_frames|k_corr_lookup_tma|k_corr_build|k_flow_warp' --csv --log-file gpurun_out/r2_launches_own_kernels.csv python profiles/ncu_bench_step.py > gpurun_out/ncu_step.log 2>&1; tail -3 gpurun_out/ncu_step.log; wc -l gpurun_out/r2_launches_own_kernels.csv
+timeout 300 python bench.py --steps 6 --warmup 3 --no-strong --no-gpu-reference --no-cpu-baseline --clips-in-flight 2 > gpurun_out/bench_c2fl.log 2> gpurun_out/bench_c2fl.err; python - <<PY
+import json
+for l in open("gpurun_out/bench_c2fl.log"):
+    if l.startswith("{"):
+        d = json.loads(l); print(round(d["value"], 1), "fps", round(d["ms_per_step"], 1), "ms e2e", round(d["e2e"]["value"], 1), d.get("single_clip"), d["clocks"], d["config"]["clips_in_flight"])
+PY
+tail -2 gpurun_out/bench_c2fl.err | cut -c1-300
