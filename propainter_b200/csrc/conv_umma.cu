@@ -284,11 +284,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
       auto finish = [&](auto actf) {
         float4 a[8];
 #pragma unroll
-#ifdef CV_DBG_NOLDS
-        for (int i = 0; i < 8; ++i) a[i] = make_float4(1.f, 2.f, 3.f, (float)i);
-#else
         for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * c4);
-#endif
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           a[i].x = actf(a[i].x + (bv.x + pv[i].x)) + rv[i].x; a[i].y = actf(a[i].y + (bv.y + pv[i].y)) + rv[i].y;
@@ -301,11 +297,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) k_conv_umma(const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-#ifdef CV_DBG_NOSTG
-          if (((on >> i) & 1) && a[i].x == 12345.678f) *reinterpret_cast<float4*>(orow[i] + ch * 32) = a[i];
-#else
           if ((on >> i) & 1) *reinterpret_cast<float4*>(orow[i] + ch * 32) = a[i];
-#endif
       };
       if (act == 0) finish([](float v) { return v; });
       else if (act == 1) finish([](float v) { return fmaxf(v, 0.f); });
