@@ -69,7 +69,7 @@ def test_sharded_pipeline_matches_single_process(tmp_path, hostsim, world, T, su
     """(2 ranks, T=13, subvideo_length=6): several units in every stage and a seam between the ranks; (3 ranks, T=17, one
     sub-video): the two flow directions of the single completion unit run on different ranks, the middle rank both receives
     and forwards seam frames; (4 ranks, T=25, 5 sub-videos): ten completion tasks spread over the ranks, halos from
-    non-adjacent owners (the 8-rank case T=41 was checked the same way by hand).  Point-to-point exchanges only; the result must equal the single-process run bit for bit."""
+    non-adjacent owners (the 8-rank case T=41 was run the same way once: bit-equal).  Point-to-point exchanges only; the result must equal the single-process run bit for bit."""
     out = str(tmp_path / "res.npz")
     mp.spawn(_worker, args=(world, _free_port(), T, sub, out), nprocs=world, join=True)
     r = np.load(out)
